@@ -1,0 +1,211 @@
+/*
+ * stx.h -- C ABI of libstoixb200.so: the B200-native kernels behind Stoix's Anakin ff_ppo hot path.
+ *
+ * The reference (EdanToledo/Stoix) has no FFI/plugin registry: its boundary is Python-level
+ * (SURVEY.md section 8b).  This header is the C boundary a maintainer binds (ctypes stub in
+ * INTEGRATION.md) to replace the JAX/XLA implementation of each reference function cited below.
+ * All paths are relative to the reference checkout.
+ *
+ * Conventions (every entry point):
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked "host";
+ *   - no allocation, no synchronisation, no host<->device copy inside; work is enqueued on the
+ *     `stream` argument (a cudaStream_t passed as void*), so every call is CUDA-graph capturable;
+ *   - return 0 on success, <0 for an invalid argument (STX_E_*), >0 for a cudaError_t;
+ *     stx_last_error_string() describes the last failure on the calling thread;
+ *   - re-entrant per stream; scratch/workspace buffers must not be shared by concurrent streams.
+ *   - tensors are row-major and time-major: a (T, E) trajectory field has flat index t*E + e,
+ *     matching merge_leading_dims (stoix/utils/jax_utils.py:29-43).
+ */
+#ifndef STX_H_
+#define STX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STX_VERSION 100 /* major*100 + minor */
+
+#define STX_OK 0
+#define STX_E_ARG (-1)      /* null pointer / negative size */
+#define STX_E_SHAPE (-2)    /* unsupported shape for this kernel */
+#define STX_E_ALIGN (-3)    /* pointer or leading dimension not aligned as required */
+#define STX_E_UNSUPPORTED (-4)
+#define STX_E_WORKSPACE (-5) /* workspace too small */
+
+#define STX_MAX_LAYERS 4 /* Dense layers per network (hidden layers + head) */
+
+/* Compute precision of the MLP GEMMs. */
+#define STX_PREC_F32 0  /* fp32 CUDA-core GEMMs: the parity path (reference is fp32 everywhere) */
+#define STX_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 master weights */
+
+/*
+ * One feed-forward network = MLPTorso(relu, activate_final) + Dense head
+ * (stoix/networks/torso.py:12-33, heads.py:30-41 CategoricalHead, heads.py:129-134 ScalarCriticHead;
+ * composed by FeedForwardActor / FeedForwardCritic, stoix/networks/base.py:18-59).
+ * `params` is a flat fp32 arena: for layer i: W_i (sizes[i] x sizes[i+1], row-major, the flax
+ * (in, out) kernel layout, y = x @ W + b) immediately followed by b_i (sizes[i+1]).
+ */
+typedef struct StxMlp {
+  int32_t n_layers;                   /* Dense layers including the head, 1..STX_MAX_LAYERS */
+  int32_t sizes[STX_MAX_LAYERS + 1];  /* sizes[0] = input dim, sizes[n_layers] = head width */
+  const float* params;                /* fp32 arena, stx_mlp_param_count() floats */
+  const void* params_bf16;            /* bf16 shadow arena (same layout), STX_PREC_BF16 only; may be NULL for F32 */
+} StxMlp;
+
+/* Hyper-parameters of _actor_loss_fn / _critic_loss_fn
+ * (stoix/systems/ppo/anakin/ff_ppo.py:191-235; configs/system/ppo/ff_ppo.yaml:6-22). */
+typedef struct StxPpoHyper {
+  float clip_eps;
+  float ent_coef;
+  float vf_coef;
+  int32_t standardize_advantages; /* 1: use (adv - stats[0]) * stats[1] on load (multistep.py:138-139) */
+} StxPpoHyper;
+
+/* One optimiser = optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps=1e-5))
+ * (ff_ppo.py:449-463) over one contiguous segment of the flat arenas. */
+typedef struct StxAdamSeg {
+  int64_t offset;      /* first float of the segment in the arenas (multiple of 4) */
+  int64_t count;       /* floats in the segment (padding excluded or zero-filled) */
+  float init_lr;       /* system.actor_lr / critic_lr */
+  float max_grad_norm; /* system.max_grad_norm */
+} StxAdamSeg;
+
+typedef struct StxAdamHyper {
+  float b1, b2, eps;         /* optax.adam defaults 0.9 / 0.999, eps=1e-5 at ff_ppo.py:458,462 */
+  float grad_scale;          /* grads are multiplied by this before clipping (1/world for a summed all-reduce) */
+  int32_t decay;             /* system.decay_learning_rates: lr(k) = init_lr*(1-(k // steps_per_update)/num_updates), utils/training.py:24-26 */
+  int32_t steps_per_update;  /* epochs * num_minibatches */
+  int32_t num_updates;       /* arch.num_updates */
+} StxAdamHyper;
+
+/* ---------------------------------------------------------------------------------------------- */
+int stx_version(void);
+const char* stx_last_error_string(void);
+/* Floats in one network arena (no padding). */
+int64_t stx_mlp_param_count(const StxMlp* mlp);
+
+/* ------------------------------------------------------------------ K2: GAE -------------------
+ * Replaces batch_truncated_generalized_advantage_estimation, stoix/utils/multistep.py:14-145, in the
+ * time-major form ff_ppo calls (ff_ppo.py:164-179).
+ *
+ * stx_gae_ppo_f32: inputs exactly as ff_ppo feeds them -- reward (T,E) f32, value = v_tm1 (T,E),
+ * bootstrap_value = v_t (T,E), done / truncated (T,E) uint8 (0/1).  Computes
+ *   r = reward*reward_scale; disc = (1-done)*gamma; delta = r + disc*v_t - v_tm1
+ *   acc_t = delta_t + disc_t*lambda*acc_{t+1}*(1-trunc_t)  (reverse in t, acc_T = 0)
+ *   adv = acc; targets = v_tm1 + adv.
+ * standardize: 0 = none; 1 = also write stats[0]=mean(adv), stats[1]=rsqrt(E[adv^2]-mean^2+1e-5)
+ *   (jax.nn.standardize over the whole (T,E) shard) leaving adv raw -- the PPO kernels apply it on
+ *   load; 2 = as 1 and adv is standardised in place (materialised, +8 B/element).
+ * scratch: >= stx_gae_scratch_bytes(T,E) bytes, zero-initialised once by the caller, reusable.
+ */
+size_t stx_gae_scratch_bytes(int T, int E);
+int stx_gae_ppo_f32(const float* reward, const float* v_tm1, const float* v_t, const uint8_t* done,
+                    const uint8_t* truncated, int T, int E, float gamma, float lambda_,
+                    float reward_scale, int standardize, float* adv, float* targets, float* stats,
+                    void* scratch, void* stream);
+/* Generic face of the same function: float discount_t (T,E), optional per-element lambda (NULL ->
+ * scalar lambda_), optional float truncation_t (NULL -> zeros).  Same outputs. */
+int stx_gae_generic_f32(const float* r_t, const float* discount_t, const float* lambda_t,
+                        float lambda_, const float* v_tm1, const float* v_t,
+                        const float* truncation_t, int T, int E, int standardize, float* adv,
+                        float* targets, float* stats, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ K1: MLP forward -----------
+ * Replaces FeedForwardActor/FeedForwardCritic.apply (stoix/networks/base.py:18-59) for MLP torsos.
+ * x: (M, sizes[0]) f32 (STX_PREC_F32) or bf16 (STX_PREC_BF16), row stride ldx elements; row_idx
+ * (nullable) gathers rows: row m reads x[row_idx[m]].  out: (M, sizes[n_layers]) f32.
+ * workspace >= stx_mlp_forward_workspace_bytes(...).
+ */
+size_t stx_mlp_forward_workspace_bytes(const StxMlp* mlp, int64_t M, int precision);
+int stx_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t* row_idx,
+                    int64_t M, float* out, int precision, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Categorical head ops on logits (E, A) -- tfd.Categorical (stoix/networks/heads.py:41) as used at
+ * ff_ppo.py:100-101.  If sample != 0: action = argmax_j(logits_j + Gumbel_j) with Philox4x32-10
+ * keyed by seed with counter (row, call = offset + *dev_counter); else `action` is an input.
+ * dev_counter (nullable device uint64) lets a captured CUDA graph draw fresh numbers on every
+ * replay: the caller bumps it with stx_counter_add at the end of the graph.  Always writes
+ * log_prob = log_softmax(logits)[action]; entropy (nullable) = -sum p log p. */
+int stx_categorical(const float* logits, int64_t E, int A, int sample, uint64_t seed,
+                    uint64_t offset, const uint64_t* dev_counter, int32_t* action, float* log_prob,
+                    float* entropy, void* stream);
+
+/* ------------------------------------------------------------------ K3: PPO minibatch grads ---
+ * Replaces the body of _update_minibatch up to (not including) the pmean: ff_ppo.py:184-247 with
+ * ppo_clip_loss / clipped_value_loss (stoix/utils/loss.py:17-32, 68-78).  For minibatch rows
+ * idx = perm[mb_off : mb_off+mb] of the flat (T*E) batch it re-runs both networks on obs[idx],
+ * evaluates the two losses and ACCUMULATES d(total_loss)/d(params) into grad_arena (caller zeroes
+ * it; layout = [actor arena | pad to 4 | critic arena], see stx_ppo_arena_offsets).
+ * metrics[6] += {actor_loss, entropy, value_loss, mean(adv used), mean(pred value), mean(target)}.
+ * obs: (B, D) f32 or bf16 per `precision`; perm NULL -> identity.
+ */
+typedef struct StxPpoBatch {
+  const void* obs;          /* (B, D) */
+  const int32_t* action;    /* (B) */
+  const float* log_prob;    /* (B) behaviour log-prob, traj_batch.log_prob */
+  const float* value;       /* (B) behaviour value, traj_batch.value */
+  const float* advantages;  /* (B) raw (standardised on load if hyper says so) */
+  const float* targets;     /* (B) */
+  const float* adv_stats;   /* [mean, rstd] from stx_gae_*; NULL if not standardising */
+  const int32_t* perm;      /* (B) permutation of the flat index, or NULL */
+  int64_t B;
+} StxPpoBatch;
+
+/* workspace: >= stx_ppo_workspace_bytes(); its first 256 bytes must be zero on first use (the
+ * kernels restore them), e.g. allocate it zero-filled once. */
+void stx_ppo_arena_offsets(const StxMlp* actor, const StxMlp* critic, int64_t* actor_off,
+                           int64_t* critic_off, int64_t* total);
+size_t stx_ppo_workspace_bytes(const StxMlp* actor, const StxMlp* critic, int64_t mb, int precision);
+int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* batch,
+                            int64_t mb_off, int64_t mb, const StxPpoHyper* hyper, float grad_weight,
+                            float* grad_arena, float* metrics, int precision, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K4: clip + Adam -----------
+ * Replaces optax.chain(clip_by_global_norm, adam) .update + optax.apply_updates for all segments in
+ * one launch (ff_ppo.py:264-273).  counts: int32[2*nseg] = {adam count, schedule count} per segment,
+ * kept on the device so the step is graph-replayable.  params_bf16 (nullable): bf16 shadow arena
+ * refreshed in the same pass.  segs: DEVICE pointer to nseg StxAdamSeg.  gnorm_out (nullable):
+ * float[nseg] pre-clip global norms.  scratch: >= stx_adam_scratch_bytes(nseg), zeroed once.
+ */
+size_t stx_adam_scratch_bytes(int nseg);
+int stx_clip_adam_step(float* param_arena, const float* grad_arena, float* mu, float* nu,
+                       int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper,
+                       void* params_bf16, float* gnorm_out, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ shuffle -------------------
+ * perm[i] = keyed bijection of [0, n) (cycle-walking Feistel over Philox rounds) replacing
+ * jax.random.permutation + jnp.take (ff_ppo.py:294-303): the minibatch kernels gather through perm,
+ * no shuffled copy of the batch is ever materialised. */
+int stx_make_permutation(int32_t* perm, int64_t n, uint64_t seed, uint64_t stream_id,
+                         const uint64_t* dev_counter, void* stream);
+/* *counter += inc on the stream (device-resident RNG stream positions for graph replay). */
+int stx_counter_add(uint64_t* counter, uint64_t inc, void* stream);
+
+/* ------------------------------------------------------------------ synthetic Box env ---------
+ * The named benchmark environment (BASELINE.json configs[1]): obs ~ N(0,1)^D,
+ * reward ~ N(0,1), terminated ~ Bernoulli(p_term), truncated = !terminated & Bernoulli(p_trunc),
+ * with stoa's AutoResetWrapper(next_obs_in_extras) + RecordEpisodeMetrics semantics
+ * (stoix/utils/make_env.py:29-61, stoix/wrappers/envpool.py:94-133):
+ *   next_obs  = true successor observation (extras["next_obs"]),
+ *   obs_out   = reset observation where the episode ended, else next_obs,
+ *   ep_return/ep_length running totals, published with is_terminal on the last step.
+ * obs buffers are f32 or bf16 per obs_bf16.  Philox counter = (env, step + *dev_counter).
+ */
+int stx_synth_env_step(int64_t E, int D, uint64_t seed, uint64_t step, const uint64_t* dev_counter,
+                       float p_term, float p_trunc, const int32_t* action, void* obs_out, void* next_obs, int obs_bf16,
+                       float* reward, uint8_t* done, uint8_t* truncated, float* run_return,
+                       int32_t* run_length, float* ep_return, int32_t* ep_length,
+                       uint8_t* is_terminal, void* stream);
+
+/* Utility casts used by the bf16 path (obs / weight shadows). */
+int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STX_H_ */

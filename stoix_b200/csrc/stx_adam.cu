@@ -1,0 +1,197 @@
+// K4 -- fused multi-segment global-norm clip + Adam + LR schedule + apply (+ bf16 weight shadow).
+//
+// Reference: optax.chain(optax.clip_by_global_norm(max_grad_norm), optax.adam(lr, eps=1e-5)) built at
+// stoix/systems/ppo/anakin/ff_ppo.py:449-463 and applied at :264-273 (update + apply_updates), with
+// the linear schedule of stoix/utils/training.py:24-26.  optax (0.2.7.dev0 @17411bc) is not vendored
+// in the reference; the arithmetic below restates its published definitions:
+//   g_norm = sqrt(sum g^2) over the segment;  g <- g              if g_norm <  max_norm
+//                                              g <- g/g_norm*max  otherwise
+//   mu = b1*mu + (1-b1)*g ; nu = b2*nu + (1-b2)*g^2 ; c = count+1
+//   u  = (mu/(1-b1^c)) / (sqrt(nu/(1-b2^c)) + eps)
+//   lr = init_lr * (1 - (sched_count // steps_per_update) / num_updates)    [read before increment]
+//   p  = p - lr*u
+// The reference launches dozens of tiny XLA fusions per optimiser (12 leaves x 2 networks); here it
+// is ONE launch over the flat arena for all segments (actor and critic are separate optimisers =
+// separate segments, clipped separately).  Phase 1 writes per-block sum-of-squares partials, a
+// software grid barrier (grid <= co-resident capacity) separates it from phase 2, which re-reduces
+// the partials in a fixed order (deterministic) and applies the update with 128-bit accesses.
+#include "stx_common.cuh"
+
+namespace stx {
+namespace {
+
+constexpr int kAdamThreads = 256;
+constexpr int kAdamMaxSegs = 8;
+
+struct AdamScratch {
+  unsigned long long arrive;  // monotonically increasing barrier ticket
+  unsigned long long pad;
+  // followed by double partials[kAdamMaxSegs][grid]
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(arrive, 1ull);
+    const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
+    while (*reinterpret_cast<volatile unsigned long long*>(arrive) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kAdamThreads)
+    clip_adam_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ MU,
+                     float* __restrict__ NU, int32_t* __restrict__ counts,
+                     const StxAdamSeg* __restrict__ segs, int nseg, StxAdamHyper h,
+                     __nv_bfloat16* __restrict__ P16, float* __restrict__ gnorm_out,
+                     AdamScratch* scratch) {
+  double* partials = reinterpret_cast<double*>(scratch + 1);
+  __shared__ double sred[32];
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gthreads = gridDim.x * blockDim.x;
+
+  // ---- phase 1: per-segment sum of squares of (grad * grad_scale) ----
+  for (int s = 0; s < nseg; ++s) {
+    const StxAdamSeg seg = segs[s];
+    const float4* g4 = reinterpret_cast<const float4*>(G + seg.offset);
+    const int64_t n4 = seg.count / 4;
+    float acc = 0.f;
+    for (int64_t i = gtid; i < n4; i += gthreads) {
+      float4 g = g4[i];
+      g.x *= h.grad_scale, g.y *= h.grad_scale, g.z *= h.grad_scale, g.w *= h.grad_scale;
+      acc += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    }
+    for (int64_t i = n4 * 4 + gtid; i < seg.count; i += gthreads) {
+      const float g = G[seg.offset + i] * h.grad_scale;
+      acc += g * g;
+    }
+    const double bs = block_sum<double>((double)acc, sred);
+    if (threadIdx.x == 0) partials[(int64_t)s * gridDim.x + blockIdx.x] = bs;
+  }
+  // counts are read before the barrier and written (by block 0) after it: no intra-launch race.
+  int32_t cnt[kAdamMaxSegs], sch[kAdamMaxSegs];
+  for (int s = 0; s < nseg; ++s) cnt[s] = counts[2 * s], sch[s] = counts[2 * s + 1];
+
+  grid_barrier(&scratch->arrive);
+
+  // ---- phase 2 ----
+  for (int s = 0; s < nseg; ++s) {
+    const StxAdamSeg seg = segs[s];
+    double ss = 0.0;
+    const volatile double* vp = partials + (int64_t)s * gridDim.x;
+    for (unsigned int b = 0; b < gridDim.x; ++b) ss += vp[b];  // same order in every block
+    const float g_norm = (float)sqrt(ss);
+    // optax.clip_by_global_norm: trigger = g_norm < max_norm
+    const float clip = (g_norm < seg.max_grad_norm) ? 1.0f : seg.max_grad_norm / g_norm;
+    const float gs = h.grad_scale * clip;
+    const int32_t c = cnt[s] + 1;
+    const float bc1 = 1.0f - powf(h.b1, (float)c);
+    const float bc2 = 1.0f - powf(h.b2, (float)c);
+    float lr = seg.init_lr;
+    if (h.decay) {
+      const int32_t k = sch[s] / h.steps_per_update;  // floor division, utils/training.py:25
+      lr = seg.init_lr * (1.0f - (float)k / (float)h.num_updates);
+    }
+    const float ob1 = 1.0f - h.b1, ob2 = 1.0f - h.b2;
+    float* p = P + seg.offset;
+    float* mu = MU + seg.offset;
+    float* nu = NU + seg.offset;
+    const float* g = G + seg.offset;
+    const int64_t n4 = seg.count / 4;
+    for (int64_t i = gtid; i < n4; i += gthreads) {
+      float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
+      float4 pv = reinterpret_cast<float4*>(p)[i];
+      float ge[4] = {gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs};
+      float me[4] = {m.x, m.y, m.z, m.w}, ve[4] = {v.x, v.y, v.z, v.w}, pe[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        me[k] = h.b1 * me[k] + ob1 * ge[k];
+        ve[k] = h.b2 * ve[k] + ob2 * ge[k] * ge[k];
+        const float u = (me[k] / bc1) / (sqrtf(ve[k] / bc2) + h.eps);
+        pe[k] = pe[k] - lr * u;
+      }
+      reinterpret_cast<float4*>(mu)[i] = make_float4(me[0], me[1], me[2], me[3]);
+      reinterpret_cast<float4*>(nu)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+      reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      if (P16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pe[0], pe[1]), hi = __floats2bfloat162_rn(pe[2], pe[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(P16 + seg.offset)[i] = pk;
+      }
+    }
+    for (int64_t i = n4 * 4 + gtid; i < seg.count; i += gthreads) {
+      const float ge = g[i] * gs;
+      const float me = h.b1 * mu[i] + ob1 * ge;
+      const float ve = h.b2 * nu[i] + ob2 * ge * ge;
+      const float u = (me / bc1) / (sqrtf(ve / bc2) + h.eps);
+      const float pn = p[i] - lr * u;
+      mu[i] = me, nu[i] = ve, p[i] = pn;
+      if (P16) P16[seg.offset + i] = __float2bfloat16_rn(pn);
+    }
+    if (gtid == 0) {
+      counts[2 * s] = c;
+      counts[2 * s + 1] = sch[s] + 1;
+      if (gnorm_out) gnorm_out[s] = g_norm;
+    }
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+int adam_grid(int64_t total) {
+  int64_t blocks = (total / 4 + kAdamThreads - 1) / kAdamThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > kNumSMs) blocks = kNumSMs;  // one wave, all blocks co-resident: the grid barrier is safe
+  return (int)blocks;
+}
+
+}  // namespace
+}  // namespace stx
+
+using namespace stx;
+
+extern "C" size_t stx_adam_scratch_bytes(int nseg) {
+  (void)nseg;
+  return sizeof(AdamScratch) + sizeof(double) * kAdamMaxSegs * kNumSMs;
+}
+
+// Host-side mirror of the segment table is needed to size the grid: callers pass the total span.
+extern "C" int stx_clip_adam_step(float* param_arena, const float* grad_arena, float* mu, float* nu,
+                                  int32_t* counts, const StxAdamSeg* segs, int nseg,
+                                  const StxAdamHyper* hyper, void* params_bf16, float* gnorm_out,
+                                  void* scratch, void* stream) {
+  STX_REQUIRE(param_arena && grad_arena && mu && nu && counts && segs && hyper && scratch, STX_E_ARG,
+              "stx_clip_adam_step: null pointer");
+  STX_REQUIRE(nseg >= 1 && nseg <= kAdamMaxSegs, STX_E_SHAPE, "stx_clip_adam_step: nseg=%d (max %d)", nseg, kAdamMaxSegs);
+  STX_REQUIRE(aligned16(param_arena) && aligned16(grad_arena) && aligned16(mu) && aligned16(nu), STX_E_ALIGN,
+              "stx_clip_adam_step: arenas must be 16-byte aligned");
+  STX_REQUIRE(hyper->steps_per_update > 0 && hyper->num_updates > 0, STX_E_ARG,
+              "stx_clip_adam_step: steps_per_update/num_updates must be positive");
+  // The grid is fixed (one wave) so the barrier ticket arithmetic is launch-invariant.
+  const int grid = kNumSMs;
+  clip_adam_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+      param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
+      reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
+  STX_LAUNCH_OK();
+  (void)adam_grid;
+  return STX_OK;
+}
+
+extern "C" int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  STX_REQUIRE(src && dst && n >= 0, STX_E_ARG, "stx_cast_f32_to_bf16: bad args");
+  if (n == 0) return STX_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  STX_LAUNCH_OK();
+  return STX_OK;
+}

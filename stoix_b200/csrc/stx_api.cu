@@ -1,0 +1,19 @@
+// Library-wide entry points: version and thread-local error string.
+#include <stdarg.h>
+
+#include "stx_common.cuh"
+
+namespace stx {
+namespace {
+thread_local char g_err[512] = "";
+}
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace stx
+
+extern "C" int stx_version(void) { return STX_VERSION; }
+extern "C" const char* stx_last_error_string(void) { return stx::g_err; }

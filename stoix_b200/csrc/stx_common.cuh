@@ -1,0 +1,144 @@
+// Shared device/host helpers for libstoixb200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/stx.h"
+
+#ifndef __CUDA_ARCH__
+#define STX_HOST_ONLY 1
+#endif
+
+namespace stx {
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const char* fmt, ...);  // defined in stx_api.cu (thread-local buffer)
+
+#define STX_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::stx::set_error(__VA_ARGS__);            \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define STX_CUDA_OK(expr)                                                         \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::stx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                       __FILE__, __LINE__);                                       \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+// Checks the launch that just happened (no sync; capture-safe).
+#define STX_LAUNCH_OK() STX_CUDA_OK(cudaPeekAtLastError())
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- Philox4x32-10 (counter-based RNG; Salmon et al. 2011) ----------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    hi = __umulhi(a, b);
+    lo = a * b;
+#else
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+  }
+  // counter = (c0..c3), key = (k0,k1) -> 4 random words
+  __host__ __device__ static inline uint4 rand4(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(M0, c.x, hi0, lo0);
+      mulhilo(M1, c.z, hi1, lo1);
+      c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+      k.x += W0;
+      k.y += W1;
+    }
+    return c;
+  }
+};
+
+// uniform in (0,1): never 0 or 1 (24-bit mantissa + half-ulp offset)
+__host__ __device__ static inline float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+#ifdef __CUDACC__
+// two N(0,1) from two words (Box-Muller, full-precision log/sincos: this is a synthetic data source
+// that the CPU test oracle re-computes, so it must not depend on -use_fast_math intrinsics).
+__device__ static inline float2 normal2(uint32_t a, uint32_t b) {
+  float r = sqrtf(-2.0f * logf(u01(a)));
+  float s, c;
+  sincospif(2.0f * u01(b), &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// ---- deterministic block reductions ---------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in thread 0. `sm` needs 32 elements. Fixed order -> deterministic.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sm) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  T r = T(0);
+  if (w == 0) {
+    r = lane < nw ? sm[lane] : T(0);
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// "Last block done" ticket: returns true in exactly one block (the last to arrive), for all of its
+// threads, after every other block's prior global writes are visible. Resets the counter for reuse.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblocks - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace stx

@@ -1,0 +1,366 @@
+"""Torch-tensor wrappers over the C ABI (include/stx.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every function below validates its
+tensors and enqueues ONE call of libstoixb200 on the current CUDA stream.  No function has a CPU or
+eager-PyTorch fallback -- a non-CUDA tensor raises StxError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import STX_PREC_BF16, STX_PREC_F32, StxError
+
+_scratch: Dict[Tuple, torch.Tensor] = {}
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise StxError("stoix_b200 ops run only on CUDA tensors (no CPU fallback exists)")
+        if not t.is_contiguous():
+            raise StxError("stoix_b200 ops need contiguous tensors")
+        dev = t.device
+    return dev
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _zeros_scratch(key: Tuple, nbytes: int, device) -> torch.Tensor:
+    """Zero-initialised scratch that persists (kernels restore their counters after use)."""
+    full = key + (str(device),)
+    t = _scratch.get(full)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _scratch[full] = t
+    return t
+
+
+@dataclass(frozen=True)
+class MlpSpec:
+    """Layer widths of one network: sizes[0] = input dim, sizes[-1] = head width."""
+
+    sizes: Tuple[int, ...]
+
+    @property
+    def n_layers(self) -> int:
+        return len(self.sizes) - 1
+
+    @property
+    def param_count(self) -> int:
+        return sum(self.sizes[i] * self.sizes[i + 1] + self.sizes[i + 1] for i in range(self.n_layers))
+
+    def layer_slices(self) -> List[Tuple[slice, slice]]:
+        out, o = [], 0
+        for i in range(self.n_layers):
+            nw = self.sizes[i] * self.sizes[i + 1]
+            out.append((slice(o, o + nw), slice(o + nw, o + nw + self.sizes[i + 1])))
+            o += nw + self.sizes[i + 1]
+        return out
+
+    def c_struct(self, params: torch.Tensor, params_bf16: Optional[torch.Tensor] = None) -> _lib.StxMlp:
+        if self.n_layers < 1 or self.n_layers > _lib.STX_MAX_LAYERS:
+            raise StxError(f"MLP with {self.n_layers} Dense layers unsupported (max {_lib.STX_MAX_LAYERS})")
+        if params.dtype != torch.float32 or params.numel() < self.param_count:
+            raise StxError("parameter arena must be float32 with at least param_count elements")
+        m = _lib.StxMlp()
+        m.n_layers = self.n_layers
+        for i, s in enumerate(self.sizes):
+            m.sizes[i] = int(s)
+        m.params = params.data_ptr()
+        m.params_bf16 = params_bf16.data_ptr() if params_bf16 is not None else None
+        return m
+
+
+def arena_offsets(actor: MlpSpec, critic: MlpSpec) -> Tuple[int, int, int]:
+    """[actor | pad to 4 floats | critic | pad] -- mirrors stx_ppo_arena_offsets."""
+    coff = (actor.param_count + 3) // 4 * 4
+    return 0, coff, coff + (critic.param_count + 3) // 4 * 4
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 GAE
+# ------------------------------------------------------------------------------------------------
+
+
+def gae_ppo(reward, value, bootstrap_value, done, truncated, gamma, gae_lambda, reward_scale=1.0,
+            standardize: int = 0, out=None):
+    """ff_ppo.py:164-179 in one launch.  Inputs (T, E); done/truncated bool or uint8.
+    Returns (advantages, targets, stats[2] or None)."""
+    dev = _need_cuda(reward, value, bootstrap_value, done, truncated)
+    T, E = reward.shape
+    for t in (reward, value, bootstrap_value):
+        if t.dtype != torch.float32 or t.shape != (T, E):
+            raise StxError("gae_ppo: reward/value/bootstrap_value must be float32 (T, E)")
+    done8 = done.view(torch.uint8) if done.dtype == torch.bool else done
+    trunc8 = truncated.view(torch.uint8) if truncated.dtype == torch.bool else truncated
+    if done8.dtype != torch.uint8 or trunc8.dtype != torch.uint8:
+        raise StxError("gae_ppo: done/truncated must be bool or uint8")
+    lib = _lib.load()
+    adv, tgt = out if out is not None else (torch.empty_like(reward), torch.empty_like(reward))
+    stats = torch.empty(2, dtype=torch.float32, device=dev) if standardize else None
+    scratch = _zeros_scratch(("gae",), lib.stx_gae_scratch_bytes(T, E), dev)
+    _lib.check(
+        lib.stx_gae_ppo_f32(_p(reward), _p(value), _p(bootstrap_value), _p(done8), _p(trunc8), T, E,
+                            float(gamma), float(gae_lambda), float(reward_scale), int(standardize),
+                            _p(adv), _p(tgt), _p(stats), _p(scratch), _stream()),
+        "stx_gae_ppo_f32",
+    )
+    return adv, tgt, stats
+
+
+def gae_generic(r_t, discount_t, lambda_, v_tm1, v_t, truncation_t=None, standardize: int = 0):
+    """Time-major generic face of multistep.py:14-145 (float discount / lambda / truncation arrays)."""
+    dev = _need_cuda(r_t, discount_t, v_tm1, v_t, truncation_t)
+    T, E = r_t.shape
+    lam_t = None
+    lam = 0.0
+    if isinstance(lambda_, torch.Tensor) and lambda_.ndim > 0:
+        lam_t = lambda_.to(torch.float32).expand(T, E).contiguous()
+        _need_cuda(lam_t)
+    else:
+        lam = float(lambda_)
+    lib = _lib.load()
+    adv, tgt = torch.empty_like(r_t), torch.empty_like(r_t)
+    stats = torch.empty(2, dtype=torch.float32, device=dev) if standardize else None
+    scratch = _zeros_scratch(("gae",), lib.stx_gae_scratch_bytes(T, E), dev)
+    _lib.check(
+        lib.stx_gae_generic_f32(_p(r_t), _p(discount_t), _p(lam_t), lam, _p(v_tm1), _p(v_t),
+                                _p(truncation_t), T, E, int(standardize), _p(adv), _p(tgt), _p(stats),
+                                _p(scratch), _stream()),
+        "stx_gae_generic_f32",
+    )
+    return adv, tgt, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 forward / categorical
+# ------------------------------------------------------------------------------------------------
+
+
+def mlp_forward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, row_idx: Optional[torch.Tensor] = None,
+                precision: int = STX_PREC_F32, params_bf16: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(params, x, row_idx, params_bf16)
+    want = torch.float32 if precision == STX_PREC_F32 else torch.bfloat16
+    if x.dtype != want or x.ndim != 2 or x.shape[1] != spec.sizes[0]:
+        raise StxError(f"mlp_forward: x must be {want} (M, {spec.sizes[0]}), got {x.dtype} {tuple(x.shape)}")
+    M = int(row_idx.numel()) if row_idx is not None else int(x.shape[0])
+    if row_idx is not None and row_idx.dtype != torch.int32:
+        raise StxError("mlp_forward: row_idx must be int32")
+    lib = _lib.load()
+    m = spec.c_struct(params, params_bf16)
+    if out is None:
+        out = torch.empty((M, spec.sizes[-1]), dtype=torch.float32, device=dev)
+    nbytes = lib.stx_mlp_forward_workspace_bytes(C.byref(m), M, precision)
+    ws = _zeros_scratch(("fwd", precision), nbytes, dev)
+    _lib.check(
+        lib.stx_mlp_forward(C.byref(m), _p(x), x.stride(0), _p(row_idx), M, _p(out), precision, _p(ws),
+                            ws.numel(), _stream()),
+        "stx_mlp_forward",
+    )
+    return out
+
+
+def categorical(logits: torch.Tensor, action: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+                dev_counter: Optional[torch.Tensor] = None, want_entropy: bool = False, out=None):
+    """Sample (action is None) or score (action given) a Categorical(logits).
+    Returns (action int32, log_prob, entropy or None)."""
+    dev = _need_cuda(logits, action, dev_counter)
+    E, A = logits.shape
+    sample = action is None
+    if out is not None:
+        action_o, logp = out
+        if sample:
+            action = action_o
+    else:
+        logp = torch.empty(E, dtype=torch.float32, device=dev)
+    if action is None:
+        action = torch.empty(E, dtype=torch.int32, device=dev)
+    if action.dtype != torch.int32:
+        raise StxError("categorical: action must be int32")
+    ent = torch.empty(E, dtype=torch.float32, device=dev) if want_entropy else None
+    lib = _lib.load()
+    _lib.check(
+        lib.stx_categorical(_p(logits), E, A, int(sample), int(seed) & (2**64 - 1), int(offset), _p(dev_counter),
+                            _p(action), _p(logp), _p(ent), _stream()),
+        "stx_categorical",
+    )
+    return action, logp, ent
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 PPO minibatch gradients
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class PpoBatch:
+    """Flat (T*E) views of the PPOTransition fields the update needs (ppo_types.py:9-20)."""
+
+    obs: torch.Tensor
+    action: torch.Tensor
+    log_prob: torch.Tensor
+    value: torch.Tensor
+    advantages: torch.Tensor
+    targets: torch.Tensor
+    adv_stats: Optional[torch.Tensor] = None
+    perm: Optional[torch.Tensor] = None
+
+    def c_struct(self) -> _lib.StxPpoBatch:
+        b = _lib.StxPpoBatch()
+        b.obs = self.obs.data_ptr()
+        b.action = self.action.data_ptr()
+        b.log_prob = self.log_prob.data_ptr()
+        b.value = self.value.data_ptr()
+        b.advantages = self.advantages.data_ptr()
+        b.targets = self.targets.data_ptr()
+        b.adv_stats = self.adv_stats.data_ptr() if self.adv_stats is not None else None
+        b.perm = self.perm.data_ptr() if self.perm is not None else None
+        b.B = int(self.action.numel())
+        return b
+
+
+def _shape_only_struct(spec: MlpSpec) -> _lib.StxMlp:
+    m = _lib.StxMlp()
+    m.n_layers = spec.n_layers
+    for i, s in enumerate(spec.sizes):
+        m.sizes[i] = int(s)
+    m.params = 256  # never dereferenced by the *_bytes queries
+    m.params_bf16 = None
+    return m
+
+
+def ppo_workspace(actor: MlpSpec, critic: MlpSpec, mb: int, precision: int, device) -> torch.Tensor:
+    """Zero-filled workspace for ppo_minibatch_grads (its first 256 bytes must start as zero)."""
+    a, c = _shape_only_struct(actor), _shape_only_struct(critic)
+    nbytes = _lib.load().stx_ppo_workspace_bytes(C.byref(a), C.byref(c), int(mb), precision)
+    return torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def ppo_minibatch_grads(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tensor, batch: PpoBatch,
+                        mb_off: int, mb: int, clip_eps: float, ent_coef: float, vf_coef: float,
+                        standardize: bool, grad_arena: torch.Tensor, metrics: torch.Tensor,
+                        workspace: torch.Tensor, precision: int = STX_PREC_F32, grad_weight: float = 1.0,
+                        param_arena_bf16: Optional[torch.Tensor] = None) -> None:
+    """Accumulate grad_weight * d(loss)/d(params) of minibatch [mb_off, mb_off+mb) into grad_arena and
+    the six loss metrics into `metrics` (ff_ppo.py:184-247)."""
+    _need_cuda(param_arena, batch.obs, batch.action, batch.log_prob, batch.value, batch.advantages,
+               batch.targets, batch.adv_stats, batch.perm, grad_arena, metrics, workspace)
+    if batch.action.dtype != torch.int32 or (batch.perm is not None and batch.perm.dtype != torch.int32):
+        raise StxError("ppo_minibatch_grads: action / perm must be int32")
+    want = torch.float32 if precision == STX_PREC_F32 else torch.bfloat16
+    if batch.obs.dtype != want:
+        raise StxError(f"ppo_minibatch_grads: obs must be {want} for precision {precision}")
+    _, coff, total = arena_offsets(actor, critic)
+    if param_arena.numel() < total or grad_arena.numel() < total or metrics.numel() < 6:
+        raise StxError("ppo_minibatch_grads: arena or metrics too small")
+    lib = _lib.load()
+    a = actor.c_struct(param_arena, param_arena_bf16)
+    c = critic.c_struct(param_arena[coff:], param_arena_bf16[coff:] if param_arena_bf16 is not None else None)
+    b = batch.c_struct()
+    h = _lib.StxPpoHyper(float(clip_eps), float(ent_coef), float(vf_coef), int(bool(standardize)))
+    _lib.check(
+        lib.stx_ppo_minibatch_grads(C.byref(a), C.byref(c), C.byref(b), int(mb_off), int(mb), C.byref(h),
+                                    float(grad_weight), _p(grad_arena), _p(metrics), precision,
+                                    _p(workspace), workspace.numel(), _stream()),
+        "stx_ppo_minibatch_grads",
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 clip + Adam
+# ------------------------------------------------------------------------------------------------
+
+
+class AdamPlan:
+    """Device-resident segment table + scratch for stx_clip_adam_step."""
+
+    def __init__(self, segments: Sequence[Tuple[int, int, float, float]], device, b1=0.9, b2=0.999, eps=1e-5,
+                 decay=True, steps_per_update=1, num_updates=1):
+        import numpy as np
+
+        self.nseg = len(segments)
+        arr = (_lib.StxAdamSeg * self.nseg)()
+        for i, (off, cnt, lr, mgn) in enumerate(segments):
+            arr[i] = _lib.StxAdamSeg(int(off), int(cnt), float(lr), float(mgn))
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.segs = torch.from_numpy(raw).to(device)
+        self.counts = torch.zeros(2 * self.nseg, dtype=torch.int32, device=device)
+        self.gnorm = torch.zeros(self.nseg, dtype=torch.float32, device=device)
+        self.scratch = torch.zeros(int(_lib.load().stx_adam_scratch_bytes(self.nseg)), dtype=torch.uint8, device=device)
+        self.hyper = _lib.StxAdamHyper(float(b1), float(b2), float(eps), 1.0, int(bool(decay)),
+                                       int(steps_per_update), int(num_updates))
+
+
+def clip_adam_step(plan: AdamPlan, params: torch.Tensor, grads: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor,
+                   grad_scale: float = 1.0, params_bf16: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(params, grads, mu, nu, params_bf16)
+    plan.hyper.grad_scale = float(grad_scale)
+    lib = _lib.load()
+    _lib.check(
+        lib.stx_clip_adam_step(_p(params), _p(grads), _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg,
+                               C.byref(plan.hyper), _p(params_bf16), _p(plan.gnorm), _p(plan.scratch), _stream()),
+        "stx_clip_adam_step",
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# shuffle / env / misc
+# ------------------------------------------------------------------------------------------------
+
+
+def make_permutation(n: int, seed: int, stream_id: int, device=None, dev_counter: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=device)
+    _need_cuda(out, dev_counter)
+    _lib.check(
+        _lib.load().stx_make_permutation(_p(out), int(n), int(seed) & (2**64 - 1), int(stream_id), _p(dev_counter), _stream()),
+        "stx_make_permutation",
+    )
+    return out
+
+
+def counter_add(counter: torch.Tensor, inc: int) -> None:
+    _need_cuda(counter)
+    if counter.dtype != torch.int64:
+        raise StxError("counter must be an int64 tensor (used as uint64)")
+    _lib.check(_lib.load().stx_counter_add(_p(counter), int(inc), _stream()), "stx_counter_add")
+
+
+def synth_env_step(E, D, seed, step, p_term, p_trunc, action, obs_out, next_obs, reward, done, truncated,
+                   run_return, run_length, ep_return, ep_length, is_terminal, dev_counter=None) -> None:
+    _need_cuda(action, obs_out, next_obs, reward, done, truncated, run_return, run_length, ep_return,
+               ep_length, is_terminal, dev_counter)
+    bf16 = obs_out.dtype == torch.bfloat16
+    if next_obs.dtype != obs_out.dtype:
+        raise StxError("synth_env_step: obs_out / next_obs dtype mismatch")
+    _lib.check(
+        _lib.load().stx_synth_env_step(int(E), int(D), int(seed) & (2**64 - 1), int(step), _p(dev_counter),
+                                       float(p_term), float(p_trunc), _p(action), _p(obs_out), _p(next_obs),
+                                       int(bf16), _p(reward), _p(done), _p(truncated), _p(run_return),
+                                       _p(run_length), _p(ep_return), _p(ep_length), _p(is_terminal), _stream()),
+        "stx_synth_env_step",
+    )
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(src)
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _lib.check(_lib.load().stx_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _stream()), "stx_cast_f32_to_bf16")
+    return out
