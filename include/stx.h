@@ -106,6 +106,8 @@ int stx_gae_ppo_f32(const float* reward, const float* v_tm1, const float* v_t, c
                     const uint8_t* truncated, int T, int E, float gamma, float lambda_,
                     float reward_scale, int standardize, float* adv, float* targets, float* stats,
                     void* scratch, void* stream);
+/* Tuning hook for experiments: force the env-quads per block (2, 4 or 8); 0 restores the heuristic. */
+void stx_gae_set_tuning(int quads);
 /* Generic face of the same function: float discount_t (T,E), optional per-element lambda (NULL ->
  * scalar lambda_), optional float truncation_t (NULL -> zeros).  Same outputs. */
 int stx_gae_generic_f32(const float* r_t, const float* discount_t, const float* lambda_t,
@@ -164,6 +166,16 @@ int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const Stx
                             int64_t mb_off, int64_t mb, const StxPpoHyper* hyper, float grad_weight,
                             float* grad_arena, float* metrics, int precision, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* Forward values of the two reference loss utilities (stoix/utils/loss.py:17-32 ppo_clip_loss,
+ * :68-78 clipped_value_loss) over n elements; out[0] = mean.  scratch >= stx_loss_scratch_bytes(),
+ * zeroed once.  (The training path uses the fused stx_ppo_minibatch_grads instead.) */
+size_t stx_loss_scratch_bytes(void);
+int stx_ppo_clip_loss(const float* pi_log_prob_t, const float* b_pi_log_prob_t, const float* gae_t,
+                      int64_t n, float epsilon, float* out, void* scratch, void* stream);
+int stx_clipped_value_loss(const float* pred_value_t, const float* behavior_value_t,
+                           const float* targets_t, int64_t n, float epsilon, float* out, void* scratch,
+                           void* stream);
 
 /* ------------------------------------------------------------------ K4: clip + Adam -----------
  * Replaces optax.chain(clip_by_global_norm, adam) .update + optax.apply_updates for all segments in

@@ -281,6 +281,25 @@ def ppo_minibatch_grads(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tens
     )
 
 
+def _loss_value(fn_name: str, a, b, c, eps: float) -> torch.Tensor:
+    dev = _need_cuda(a, b, c)
+    if not (a.dtype == b.dtype == c.dtype == torch.float32) or not (a.numel() == b.numel() == c.numel()):
+        raise StxError(f"{fn_name}: expected three float32 tensors of equal size")
+    lib = _lib.load()
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    scratch = _zeros_scratch(("loss",), lib.stx_loss_scratch_bytes(), dev)
+    _lib.check(getattr(lib, fn_name)(_p(a), _p(b), _p(c), a.numel(), float(eps), _p(out), _p(scratch), _stream()), fn_name)
+    return out[0]
+
+
+def ppo_clip_loss_value(pi_log_prob_t, b_pi_log_prob_t, gae_t, epsilon) -> torch.Tensor:
+    return _loss_value("stx_ppo_clip_loss", pi_log_prob_t, b_pi_log_prob_t, gae_t, epsilon)
+
+
+def clipped_value_loss_value(pred_value_t, behavior_value_t, targets_t, epsilon) -> torch.Tensor:
+    return _loss_value("stx_clipped_value_loss", pred_value_t, behavior_value_t, targets_t, epsilon)
+
+
 # ------------------------------------------------------------------------------------------------
 # K4 clip + Adam
 # ------------------------------------------------------------------------------------------------

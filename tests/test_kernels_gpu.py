@@ -1,0 +1,242 @@
+"""Parity of the remaining kernels against the oracle: fp32 MLP forward, Categorical head, PPO
+minibatch gradients (K3), clip+Adam (K4), shuffle, synthetic env.  fp32-kernel-vs-fp64-oracle
+tolerances are written at each assertion."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _t(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device=_dev())
+
+
+def _nets(rng, D, H, A):
+    actor = O.init_mlp(rng, [D, *H, A], 0.01)
+    critic = O.init_mlp(rng, [D, *H, 1], 1.0)
+    for p in (actor, critic):
+        for i in range(len(p.W)):
+            p.b[i] = rng.standard_normal(p.b[i].shape) * 0.1
+        p.W[-1] = rng.standard_normal(p.W[-1].shape) * 0.3
+    return actor, critic
+
+
+def _arena(actor, critic):
+    from stoix_b200 import ops
+
+    sa = ops.MlpSpec(tuple([actor.W[0].shape[0]] + [w.shape[1] for w in actor.W]))
+    sc = ops.MlpSpec(tuple([critic.W[0].shape[0]] + [w.shape[1] for w in critic.W]))
+    _, coff, total = ops.arena_offsets(sa, sc)
+    flat = np.zeros(total, np.float32)
+    flat[: sa.param_count] = actor.flat()
+    flat[coff : coff + sc.param_count] = critic.flat()
+    return sa, sc, coff, total, _t(flat)
+
+
+@pytest.mark.parametrize("M,D,H,A", [(300, 64, (256, 256), 8), (5, 4, (256, 256), 2), (1000, 17, (50, 30), 6), (64, 64, (256,), 8)])
+def test_mlp_forward_fp32(M, D, H, A):
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(M)
+    actor, _ = _nets(rng, D, H, A)
+    x = rng.standard_normal((M, D)).astype(np.float32)
+    spec = ops.MlpSpec(tuple([D, *H, A]))
+    out = ops.mlp_forward(spec, _t(actor.flat()), _t(x))
+    ref, _ = O.mlp_forward(actor, x.astype(np.float64))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-6)
+    idx = rng.permutation(M)[: max(1, M // 2)].astype(np.int32)
+    out_g = ops.mlp_forward(spec, _t(actor.flat()), _t(x), row_idx=_t(idx, torch.int32))
+    np.testing.assert_allclose(out_g.cpu().numpy(), ref[idx], rtol=2e-5, atol=2e-6)
+
+
+def test_categorical_logprob_entropy_and_sampling():
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(0)
+    E, A = 4096, 8
+    logits = (rng.standard_normal((E, A)) * 2).astype(np.float32)
+    act = rng.integers(0, A, E).astype(np.int32)
+    a, lp, ent = ops.categorical(_t(logits), action=_t(act, torch.int32), want_entropy=True)
+    np.testing.assert_allclose(lp.cpu().numpy(), O.categorical_log_prob(logits.astype(np.float64), act), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent.cpu().numpy(), O.categorical_entropy(logits.astype(np.float64)), rtol=1e-5, atol=1e-6)
+    # sampling: deterministic in (seed, offset), changes with either, frequencies match softmax
+    one = np.tile(np.array([[0.0, 1.0, 2.0, -1.0, 0.5, 0.0, -2.0, 1.5]], np.float32), (200000, 1))
+    s1, lp1, _ = ops.categorical(_t(one), seed=42, offset=3)
+    s2, _, _ = ops.categorical(_t(one), seed=42, offset=3)
+    s3, _, _ = ops.categorical(_t(one), seed=42, offset=4)
+    s4, _, _ = ops.categorical(_t(one), seed=43, offset=3)
+    assert torch.equal(s1, s2) and not torch.equal(s1, s3) and not torch.equal(s1, s4)
+    ctr = torch.ones(1, dtype=torch.int64, device=_dev())
+    s5, _, _ = ops.categorical(_t(one), seed=42, offset=2, dev_counter=ctr)  # offset 2 + counter 1 == offset 3
+    assert torch.equal(s1, s5)
+    p = np.exp(O.log_softmax(one[0].astype(np.float64)))
+    freq = np.bincount(s1.cpu().numpy(), minlength=8) / one.shape[0]
+    assert np.abs(freq - p).max() < 5e-3
+    np.testing.assert_allclose(lp1.cpu().numpy(), np.log(p)[s1.cpu().numpy()], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,mb_off,mb,D,H,A,use_perm", [
+    (2048, 512, 1024, 64, (256, 256), 8, True),
+    (64, 0, 4, 4, (256, 256), 2, True),      # BASELINE configs[0] minibatch (T=16,E=4 -> B=64, mb=4)
+    (600, 100, 333, 17, (50, 30), 6, False),  # ragged sizes, contiguous minibatch
+    (4096, 0, 4096, 64, (256, 256), 8, True),
+])
+def test_ppo_minibatch_grads_vs_oracle(B, mb_off, mb, D, H, A, use_perm):
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(B + mb)
+    actor, critic = _nets(rng, D, H, A)
+    sa, sc, coff, total, arena = _arena(actor, critic)
+    obs = rng.standard_normal((B, D)).astype(np.float32)
+    act = rng.integers(0, A, B).astype(np.int32)
+    logits, _ = O.mlp_forward(actor, obs.astype(np.float64))
+    lp_old = (O.categorical_log_prob(logits, act) + rng.standard_normal(B) * 0.3).astype(np.float32)
+    v_old = rng.standard_normal(B).astype(np.float32)
+    adv = (rng.standard_normal(B) * 2 + 0.3).astype(np.float32)
+    tgt = rng.standard_normal(B).astype(np.float32)
+    mean = adv.astype(np.float64).mean()
+    rstd = 1.0 / np.sqrt((adv.astype(np.float64) ** 2).mean() - mean * mean + 1e-5)
+    perm = rng.permutation(B).astype(np.int32) if use_perm else None
+    idx = perm[mb_off : mb_off + mb] if use_perm else np.arange(mb_off, mb_off + mb)
+    # oracle
+    adv_n = (adv.astype(np.float64) - mean) * rstd
+    lg, a_acts = O.mlp_forward(actor, obs[idx].astype(np.float64))
+    _, dlg, a_info = O.actor_loss_and_dlogits(lg, act[idx], lp_old[idx].astype(np.float64), adv_n[idx], 0.2, 0.01)
+    ga = O.mlp_backward(actor, a_acts, dlg).flat()
+    v, c_acts = O.mlp_forward(critic, obs[idx].astype(np.float64))
+    _, dv, c_info = O.critic_loss_and_dvalue(v[:, 0], v_old[idx].astype(np.float64), tgt[idx].astype(np.float64), 0.2, 0.5)
+    gc = O.mlp_backward(critic, c_acts, dv[:, None]).flat()
+    # kernel
+    batch = ops.PpoBatch(_t(obs), _t(act, torch.int32), _t(lp_old), _t(v_old), _t(adv), _t(tgt),
+                         adv_stats=_t(np.array([mean, rstd])), perm=_t(perm, torch.int32) if use_perm else None)
+    grads = torch.zeros(total, device=_dev())
+    metrics = torch.zeros(6, device=_dev())
+    ws = ops.ppo_workspace(sa, sc, mb, ops.STX_PREC_F32, _dev())
+    for _ in range(2):  # twice with weight 0.5: accumulation semantics + workspace reuse
+        ops.ppo_minibatch_grads(sa, sc, arena, batch, mb_off, mb, 0.2, 0.01, 0.5, True, grads, metrics, ws, grad_weight=0.5)
+    g = grads.cpu().numpy().astype(np.float64)
+    scale = max(np.abs(ga).max(), 1e-12)
+    np.testing.assert_allclose(g[: sa.param_count], ga, rtol=1e-4, atol=2e-6 * scale + 1e-9)
+    scale = max(np.abs(gc).max(), 1e-12)
+    np.testing.assert_allclose(g[coff : coff + sc.param_count], gc, rtol=1e-4, atol=2e-6 * scale + 1e-9)
+    mt = metrics.cpu().numpy()
+    np.testing.assert_allclose(mt[:3], [a_info["actor_loss"], a_info["entropy"], c_info["value_loss"]], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(mt[3:], [adv_n[idx].mean(), v[:, 0].mean(), tgt[idx].astype(np.float64).mean()], rtol=2e-5, atol=2e-6)
+    # run-to-run determinism (fixed-order reductions everywhere)
+    g2 = torch.zeros(total, device=_dev())
+    g3 = torch.zeros(total, device=_dev())
+    m2 = torch.zeros(6, device=_dev())
+    ops.ppo_minibatch_grads(sa, sc, arena, batch, mb_off, mb, 0.2, 0.01, 0.5, True, g2, m2, ws)
+    ops.ppo_minibatch_grads(sa, sc, arena, batch, mb_off, mb, 0.2, 0.01, 0.5, True, g3, m2, ws)
+    assert torch.equal(g2, g3)
+
+
+def test_loss_value_faces():
+    from stoix_b200.utils.loss import clipped_value_loss, ppo_clip_loss
+
+    rng = np.random.default_rng(9)
+    n = 10000
+    a, b, c = (rng.standard_normal(n).astype(np.float32) * 0.4 for _ in range(3))
+    np.testing.assert_allclose(ppo_clip_loss(_t(a), _t(b), _t(c), 0.2).item(), O.ppo_clip_loss(a.astype(np.float64), b.astype(np.float64), c.astype(np.float64), 0.2), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(clipped_value_loss(_t(a), _t(b), _t(c), 0.2).item(), O.clipped_value_loss(a.astype(np.float64), b.astype(np.float64), c.astype(np.float64), 0.2), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("grad_mag,decay", [(1e-3, True), (10.0, True), (10.0, False)])
+def test_clip_adam_vs_oracle(grad_mag, decay):
+    """64 consecutive optimiser steps (one update's worth) on two segments of unequal, non-multiple-
+    of-4 length; params after 64 steps: rtol 1e-4 / atol 1e-6."""
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(1)
+    na, nc = 84488, 82689
+    coff = (na + 3) // 4 * 4
+    total = coff + (nc + 3) // 4 * 4
+    p0 = np.zeros(total, np.float32)
+    p0[:na] = rng.standard_normal(na) * 0.1
+    p0[coff : coff + nc] = rng.standard_normal(nc) * 0.1
+    params, mu, nu = _t(p0), torch.zeros(total, device=_dev()), torch.zeros(total, device=_dev())
+    shadow = torch.zeros(total, dtype=torch.bfloat16, device=_dev())
+    num_updates, spu = 3, 16
+    plan = ops.AdamPlan([(0, na, 3e-4, 0.5), (coff, nc, 1e-3, 0.5)], _dev(), decay=decay, steps_per_update=spu, num_updates=num_updates)
+    pa, pc = p0[:na].astype(np.float64), p0[coff : coff + nc].astype(np.float64)
+    sa_, sc_ = O.AdamState(np.zeros(na), np.zeros(na)), O.AdamState(np.zeros(nc), np.zeros(nc))
+    world = 4.0
+    for step in range(40):
+        g = np.zeros(total, np.float32)
+        g[:na] = rng.standard_normal(na) * grad_mag
+        g[coff : coff + nc] = rng.standard_normal(nc) * grad_mag * (0.01 if step % 2 else 1.0)
+        ops.clip_adam_step(plan, params, _t(g), mu, nu, grad_scale=1.0 / world, params_bf16=shadow)
+        lr_a = O.linear_schedule(3e-4, sa_.sched_count, num_updates, 1, spu, decay)
+        lr_c = O.linear_schedule(1e-3, sc_.sched_count, num_updates, 1, spu, decay)
+        pa, gna = O.clip_adam_step(pa, g[:na].astype(np.float64) / world, sa_, lr_a, 0.5)
+        pc, gnc = O.clip_adam_step(pc, g[coff : coff + nc].astype(np.float64) / world, sc_, lr_c, 0.5)
+        np.testing.assert_allclose(plan.gnorm.cpu().numpy(), [gna, gnc], rtol=1e-5)
+    out = params.cpu().numpy()
+    np.testing.assert_allclose(out[:na], pa, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out[coff : coff + nc], pc, rtol=1e-4, atol=1e-6)
+    assert plan.counts.cpu().tolist() == [40, 40, 40, 40]
+    assert out[na:coff].tolist() == [0.0] * (coff - na)  # padding untouched
+    np.testing.assert_array_equal(shadow.float().cpu().numpy(), params.to(torch.bfloat16).float().cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [1, 2, 64, 1000, 524288, 300001])
+def test_permutation_is_a_bijection(n):
+    from stoix_b200 import ops
+
+    p = ops.make_permutation(n, seed=42, stream_id=0, device=_dev())
+    assert torch.equal(torch.sort(p.long()).values, torch.arange(n, device=_dev()))
+    if n >= 64:
+        q = ops.make_permutation(n, seed=42, stream_id=1, device=_dev())
+        r = ops.make_permutation(n, seed=43, stream_id=0, device=_dev())
+        assert not torch.equal(p, q) and not torch.equal(p, r)
+        ctr = torch.ones(1, dtype=torch.int64, device=_dev())
+        q2 = ops.make_permutation(n, seed=42, stream_id=0, device=_dev(), dev_counter=ctr)
+        assert torch.equal(q, q2)
+        assert not torch.equal(p.long(), torch.arange(n, device=_dev()))
+    if n == 524288:  # crude mixing check: first minibatch should be spread over the whole range
+        first = p[: n // 16].float()
+        assert abs(first.mean().item() / n - 0.5) < 0.01
+
+
+def test_synthetic_env_contract():
+    from stoix_b200 import ops
+    from oracle import synth_env as SE
+
+    E, D, seed = 512, 64, 42
+    dev = _dev()
+    obs = torch.zeros(E, D, device=dev)
+    nxt = torch.zeros(E, D, device=dev)
+    rew = torch.zeros(E, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+    trunc = torch.zeros(E, dtype=torch.uint8, device=dev)
+    rr = torch.zeros(E, device=dev)
+    rl = torch.zeros(E, dtype=torch.int32, device=dev)
+    er = torch.zeros(E, device=dev)
+    el = torch.zeros(E, dtype=torch.int32, device=dev)
+    it = torch.zeros(E, dtype=torch.uint8, device=dev)
+    act = torch.zeros(E, dtype=torch.int32, device=dev)
+    ref = SE.SynthEnvOracle(E, D, seed, p_term=0.05, p_trunc=0.1)
+    for step in range(30):
+        ops.synth_env_step(E, D, seed, step, 0.05, 0.1, act, obs, nxt, rew, done, trunc, rr, rl, er, el, it)
+        o = ref.step(step)
+        np.testing.assert_array_equal(done.cpu().numpy(), o["done"])
+        np.testing.assert_array_equal(trunc.cpu().numpy(), o["truncated"])
+        np.testing.assert_array_equal(it.cpu().numpy(), o["is_terminal"])
+        np.testing.assert_allclose(rew.cpu().numpy(), o["reward"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(nxt.cpu().numpy(), o["next_obs"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(obs.cpu().numpy(), o["obs"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(er.cpu().numpy(), o["ep_return"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(el.cpu().numpy(), o["ep_length"])
+    assert (done & trunc).sum().item() == 0
+    # bf16 observation buffers carry the same draws rounded to bf16
+    ob16 = torch.zeros(E, D, dtype=torch.bfloat16, device=dev)
+    nx16 = torch.zeros(E, D, dtype=torch.bfloat16, device=dev)
+    ops.synth_env_step(E, D, seed, 29, 0.05, 0.1, act, ob16, nx16, rew, done, trunc, rr, rl, er, el, it)
+    assert torch.equal(nx16, nxt.to(torch.bfloat16)) and torch.equal(ob16, obs.to(torch.bfloat16))
