@@ -84,6 +84,9 @@ typedef struct StxAdamHyper {
 /* ---------------------------------------------------------------------------------------------- */
 int stx_version(void);
 const char* stx_last_error_string(void);
+/* Kernel launches enqueued by this library in this process so far (host-side count; launches replayed
+ * from a captured CUDA graph are counted once, at capture). */
+unsigned long long stx_launch_count(void);
 /* Floats in one network arena (no padding). */
 int64_t stx_mlp_param_count(const StxMlp* mlp);
 

@@ -75,6 +75,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "stx_version": (C.c_int, []),
     "stx_last_error_string": (C.c_char_p, []),
+    "stx_launch_count": (C.c_ulonglong, []),
     "stx_mlp_param_count": (C.c_int64, [C.POINTER(StxMlp)]),
     "stx_gae_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "stx_gae_set_tuning": (None, [C.c_int]),

@@ -34,8 +34,13 @@ void set_error(const char* fmt, ...);  // defined in stx_api.cu (thread-local bu
     }                                                                             \
   } while (0)
 
-// Checks the launch that just happened (no sync; capture-safe).
-#define STX_LAUNCH_OK() STX_CUDA_OK(cudaPeekAtLastError())
+// Checks the launch that just happened (no sync; capture-safe) and counts it (stx_launch_count()).
+void count_launch();
+#define STX_LAUNCH_OK()                  \
+  do {                                   \
+    ::stx::count_launch();               \
+    STX_CUDA_OK(cudaPeekAtLastError());  \
+  } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(QUADS* kChunks)
   const int e0 = (blockIdx.x * QUADS + q) * VEC;
   const bool env_ok = e0 < E;
 
-  __shared__ float sA[kChunks][ENVS + 1], sB[kChunks][ENVS + 1], sIn[kChunks][ENVS + 1];
+  __shared__ float sA[kChunks][ENVS + 1], sB[kChunks][ENVS + 1];  // sA is reused for acc_in
   __shared__ float sCarry[ENVS];
   __shared__ double sRed[32];
   if (threadIdx.x < ENVS) sCarry[threadIdx.x] = 0.f;  // multistep.py:127: acc starts at zero
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(QUADS* kChunks)
       }
       const float carry = sCarry[env];
       const float Ae = __shfl_down_sync(0xffffffffu, A, 1), Be = __shfl_down_sync(0xffffffffu, B, 1);
-      sIn[lane][env] = (lane == 31) ? carry : fmaf(Ae, carry, Be);
+      sA[lane][env] = (lane == 31) ? carry : fmaf(Ae, carry, Be);  // acc entering this chunk
       __syncwarp();
       if (lane == 0) sCarry[env] = fmaf(A, carry, B);  // acc entering the previous (earlier) segment
     }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(QUADS* kChunks)
       float av[VEC], tv[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        av[k] = fmaf(a[j][k], sIn[chunk][q * VEC + k], b[j][k]);
+        av[k] = fmaf(a[j][k], sA[chunk][q * VEC + k], b[j][k]);
         tv[k] = v[j][k] + av[k];  // multistep.py:132: targets use the un-standardised advantage
       }
       if (env_ok && t < T) {
@@ -203,9 +203,15 @@ int launch_gae(const In& in, int T, int E, bool vec4, int standardize, float* ad
     const int quads_total = E / 4;
     // Small E is latency-bound: more, smaller blocks.  Large E: 128-byte rows per warp access.
     int quads = quads_total >= 8 * kNumSMs * 2 ? 8 : (quads_total >= 4 * kNumSMs ? 4 : 2);
-    if (g_quads_override == 2 || g_quads_override == 4 || g_quads_override == 8) quads = g_quads_override;
+    if (g_quads_override == 2 || g_quads_override == 4 || g_quads_override == 8 || g_quads_override == 16 ||
+        g_quads_override == 32)
+      quads = g_quads_override;
     const int grid = (quads_total + quads - 1) / quads;
-    if (quads == 8)
+    if (quads == 32)
+      gae_scan_kernel<In, 4, 32><<<grid, 32 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else if (quads == 16)
+      gae_scan_kernel<In, 4, 16><<<grid, 16 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else if (quads == 8)
       gae_scan_kernel<In, 4, 8><<<grid, 8 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
     else if (quads == 4)
       gae_scan_kernel<In, 4, 4><<<grid, 4 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);

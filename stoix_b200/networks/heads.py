@@ -1,0 +1,67 @@
+"""CategoricalHead / ScalarCriticHead -- constructor-compatible with stoix/networks/heads.py:30-41,
+129-134, and the distribution object the actor returns (tfd.Categorical's sample / log_prob /
+entropy / mode as used at ff_ppo.py:100-101,199,205)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class Categorical:
+    """Categorical(logits) backed by stx_categorical."""
+
+    def __init__(self, logits: torch.Tensor):
+        self.logits = logits
+
+    def sample(self, seed=None, offset: int = 0, dev_counter: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`seed` is an int or a PRNG key tensor (any integer tensor: its first two words are used)."""
+        s = _seed_to_int(seed)
+        a, lp, _ = ops.categorical(self.logits, None, s, offset, dev_counter)
+        self._last = (a, lp)
+        return a
+
+    def log_prob(self, action: torch.Tensor) -> torch.Tensor:
+        last = getattr(self, "_last", None)
+        if last is not None and last[0] is action:
+            return last[1]
+        _, lp, _ = ops.categorical(self.logits, action.to(torch.int32).contiguous())
+        return lp
+
+    def entropy(self) -> torch.Tensor:
+        a = torch.zeros(self.logits.shape[0], dtype=torch.int32, device=self.logits.device)
+        _, _, ent = ops.categorical(self.logits, a, want_entropy=True)
+        return ent
+
+    def mode(self) -> torch.Tensor:
+        return torch.argmax(self.logits, dim=-1).to(torch.int32)
+
+
+def _seed_to_int(seed) -> int:
+    if seed is None:
+        return 0
+    if isinstance(seed, torch.Tensor):
+        w = seed.reshape(-1).to(torch.int64).cpu().tolist()
+        return ((w[0] & 0xFFFFFFFF) << 32 | (w[-1] & 0xFFFFFFFF)) & (2**64 - 1)
+    return int(seed) & (2**64 - 1)
+
+
+class CategoricalHead:
+    def __init__(self, action_dim: Union[int, Sequence[int]], kernel_init: Optional[float] = None):
+        if not isinstance(action_dim, (int, np.integer)):
+            raise NotImplementedError("factorised action_dim is outside the B200 hot path")
+        self.action_dim = int(action_dim)
+        self.out_dim = self.action_dim
+        self.kernel_init_scale = 0.01 if kernel_init is None else float(kernel_init)  # heads.py:32
+
+    def distribution(self, logits: torch.Tensor) -> Categorical:
+        return Categorical(logits)
+
+
+class ScalarCriticHead:
+    def __init__(self, kernel_init: Optional[float] = None):
+        self.out_dim = 1
+        self.kernel_init_scale = 1.0 if kernel_init is None else float(kernel_init)  # heads.py:130

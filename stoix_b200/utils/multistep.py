@@ -39,8 +39,6 @@ def batch_truncated_generalized_advantage_estimation(
     """
     del stop_target_gradients
     # multistep.py:77-92 -- the same argument validation, as assertions.
-    if truncation_t is not None:
-        assert _is_float(v_tm1) and _is_float(v_t), "truncation_t requires float v_tm1 and v_t"
     if values is None:
         assert _is_float(v_tm1) and _is_float(v_t), "either `values` or both v_tm1 and v_t are required"
     else:
