@@ -281,8 +281,8 @@ def run_ours(args):
 
     # ---- timed region B: end to end through the public API with host buffers (e2e) ----
     sh = learn.built["shards"][0]
-    host_obs = torch.empty(sh.obs[0].shape, dtype=sh.obs.dtype).pin_memory()
-    host_obs.copy_(sh.obs[0])
+    host_obs = torch.empty(sh.obs[T].shape, dtype=sh.obs.dtype).pin_memory()
+    host_obs.copy_(sh.obs[T])
     host_train = torch.empty(EPOCHS, NMB, len(ff_ppo._METRIC_NAMES), dtype=torch.float32).pin_memory()
     host_ret = torch.empty(T, E_PER_GPU, dtype=torch.float32).pin_memory()
     host_term = torch.empty(T, E_PER_GPU, dtype=torch.bool).pin_memory()
@@ -292,14 +292,14 @@ def run_ours(args):
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for _ in range(args.steps):
-        sh.obs[0].copy_(host_obs, non_blocking=True)      # H2D: the step's input observations (pinned)
+        sh.obs[T].copy_(host_obs, non_blocking=True)      # H2D: the step's input observations (pinned)
         out = learn(state)
         state = out.learner_state
         host_train.copy_(torch.stack([out.train_metrics[n][0] for n in ff_ppo._METRIC_NAMES], -1), non_blocking=True)
         host_ret.copy_(out.episode_metrics["episode_return"][0, 0], non_blocking=True)
         host_term.copy_(out.episode_metrics["is_terminal_step"][0, 0], non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the host consumes the step's result
-        host_obs.copy_(sh.obs[0])                         # keep the trajectory continuous for the next upload
+        host_obs.copy_(sh.obs[T])                         # D2H: the observation the next step starts from
     ev3.record()
     barrier()
     dt_e2e = ev2.elapsed_time(ev3) * 1e-3

@@ -43,7 +43,7 @@ def bench(T, E, quads=0, iters=20, flush=True):
 if __name__ == "__main__":
     out = []
     for (T, E) in [(128, 4096), (128, 65536), (128, 1048576)]:
-        for q in (0, 8, 16, 32):
+        for q in (0, 8, 32, 216, 232):
             for fl in (True, False):
                 if not fl and E > 65536:
                     continue

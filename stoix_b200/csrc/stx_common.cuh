@@ -139,6 +139,19 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream2(float* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_stream_u16(const void* p) {
+  uint16_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
   uint32_t r;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));

@@ -39,6 +39,15 @@ struct PpoIn {  // exactly what ff_ppo.py:164-169 feeds
         dn[k] = ((fd >> (8 * k)) & 0xffu) ? 1.f : 0.f;
         tr[k] = ((ft >> (8 * k)) & 0xffu) ? 1.f : 0.f;
       }
+    } else if constexpr (VEC == 2) {
+      float2 a = ldg_stream2(reward + off), b = ldg_stream2(v_tm1 + off), e = ldg_stream2(v_t + off);
+      uint32_t fd = ldg_stream_u16(done + off), ft = ldg_stream_u16(trunc + off);
+      r[0] = a.x, r[1] = a.y, v[0] = b.x, v[1] = b.y, vt[0] = e.x, vt[1] = e.y;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        dn[k] = ((fd >> (8 * k)) & 0xffu) ? 1.f : 0.f;
+        tr[k] = ((ft >> (8 * k)) & 0xffu) ? 1.f : 0.f;
+      }
     } else {
       r[0] = __ldg(reward + off), v[0] = __ldg(v_tm1 + off), vt[0] = __ldg(v_t + off);
       dn[0] = __ldg(done + off) ? 1.f : 0.f, tr[0] = __ldg(trunc + off) ? 1.f : 0.f;
@@ -152,6 +161,9 @@ __global__ void __launch_bounds__(QUADS* kChunks)
         if constexpr (VEC == 4) {
           stg_stream4(adv + off, make_float4(av[0], av[1], av[2], av[3]));
           stg_stream4(tgt + off, make_float4(tv[0], tv[1], tv[2], tv[3]));
+        } else if constexpr (VEC == 2) {
+          stg_stream2(adv + off, make_float2(av[0], av[1]));
+          stg_stream2(tgt + off, make_float2(tv[0], tv[1]));
         } else {
           adv[off] = av[0];
           tgt[off] = tv[0];
@@ -199,7 +211,14 @@ int launch_gae(const In& in, int T, int E, bool vec4, int standardize, float* ad
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double2* partials = reinterpret_cast<double2*>(reinterpret_cast<char*>(scratch) + 16);
   const int want = standardize != 0;
-  if (vec4) {
+  if (vec4 && g_quads_override / 100 == 2) {  // experimental float2 variants: tuning code 2xx
+    const int groups = g_quads_override % 100, total = E / 2;
+    const int grid = (total + groups - 1) / groups;
+    if (groups == 32)
+      gae_scan_kernel<In, 2, 32><<<grid, 32 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else
+      gae_scan_kernel<In, 2, 16><<<grid, 16 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+  } else if (vec4) {
     const int quads_total = E / 4;
     // Small E is latency-bound: more, smaller blocks.  Large E: 128-byte rows per warp access.
     int quads = quads_total >= 8 * kNumSMs * 2 ? 8 : (quads_total >= 4 * kNumSMs ? 4 : 2);

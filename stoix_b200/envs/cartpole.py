@@ -23,8 +23,7 @@ class CartPoleEnv(Environment):
 
     def __init__(self, device="cuda", seed: int = 0):
         self.device = torch.device(device)
-        self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(int(seed))
+        self.seed = int(seed)  # reset states come from torch's default CUDA generator (CUDA-graph safe)
 
     def observation_space(self) -> ArraySpace:
         return ArraySpace((4,), torch.float32, self.device)
@@ -33,7 +32,7 @@ class CartPoleEnv(Environment):
         return DiscreteSpace(2)
 
     def _fresh(self, E: int) -> torch.Tensor:
-        return (torch.rand(E, 4, device=self.device, generator=self.gen) - 0.5) * 0.1
+        return (torch.rand(E, 4, device=self.device) - 0.5) * 0.1
 
     def reset(self, keys) -> Tuple[Dict[str, Any], TimeStep]:
         E, dev = len(keys), self.device

@@ -33,6 +33,7 @@ class SyntheticBoxEnv(Environment):
         E = len(keys)
         dev = self.device
         state = {
+            "seed": int(self.seed),  # per-shard stream: learner_setup sets env.seed before each reset
             "counter": torch.zeros(1, dtype=torch.int64, device=dev),  # global step index (uint64)
             "run_return": torch.zeros(E, dtype=torch.float32, device=dev),
             "run_length": torch.zeros(E, dtype=torch.int32, device=dev),
@@ -76,7 +77,7 @@ class SyntheticBoxEnv(Environment):
     def step_into(self, state, action: torch.Tensor, out: StepOut, t: int) -> None:
         """Step `t` (offset added to the device-resident counter) writing into `out`."""
         E = state["run_return"].shape[0]
-        ops.synth_env_step(E, self.obs_dim, self.seed, int(t), self.p_term, self.p_trunc, action, out.obs, out.next_obs,
+        ops.synth_env_step(E, self.obs_dim, state["seed"], int(t), self.p_term, self.p_trunc, action, out.obs, out.next_obs,
                            out.reward, out.done, out.truncated, state["run_return"], state["run_length"],
                            out.episode_return, out.episode_length, out.is_terminal_step, dev_counter=state["counter"])
 

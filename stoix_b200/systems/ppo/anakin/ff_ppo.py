@@ -241,12 +241,17 @@ def get_learner_fn(
             dist.all_reduce(metrics, op=dist.ReduceOp.SUM)
             metrics.mul_(1.0 / world)
 
-    def _carry_phase(state: OnPolicyLearnerState) -> None:
-        """The last observation becomes the first of the next rollout; advance the RNG streams."""
+    def _carry_in_phase(state: OnPolicyLearnerState) -> None:
+        """The latest observation (row T of the previous rollout) is the first of this rollout
+        (learner_state.timestep of ff_ppo.py:131-134); the finished trajectory stays readable until then."""
+        for u in range(U):
+            sh = built["shards"][u]
+            sh.obs[0].copy_(sh.obs[T])
+
+    def _advance_phase(state: OnPolicyLearnerState) -> None:
+        """Advance the device-resident RNG stream positions (graph replays then draw fresh numbers)."""
         b = built
         for u in range(U):
-            sh = b["shards"][u]
-            sh.obs[0].copy_(sh.obs[T])
             if hasattr(env, "advance"):
                 env.advance(state.env_state[u], T)
         ops.counter_add(b["roll_ctr"], T)
@@ -254,10 +259,11 @@ def get_learner_fn(
 
     def _update_step(state: OnPolicyLearnerState) -> None:
         """A single update of the network (ff_ppo.py:61-341), in place on the learner state."""
+        _carry_in_phase(state)
         _rollout_phase(state)
         _gae_phase(state)
         _update_phase(state)
-        _carry_phase(state)
+        _advance_phase(state)
 
     def learner_fn(learner_state: OnPolicyLearnerState) -> AnakinExperimentOutput[OnPolicyLearnerState]:
         """Run arch.num_updates_per_eval update steps (ff_ppo.py:343-370)."""
@@ -290,15 +296,22 @@ def get_learner_fn(
                 ep_out["is_terminal_step"][k, u].copy_(sh.is_terminal_step)
             train_out[k].copy_(b["metrics"])
         # the observation the next learn() call starts from
-        new_ts = [learner_state.timestep[u]._replace(observation=b["shards"][u].obs[0]) for u in range(U)]
+        new_ts = [learner_state.timestep[u]._replace(observation=b["shards"][u].obs[T]) for u in range(U)]
         learner_state = learner_state._replace(timestep=new_ts)
         train_metrics = {name: train_out[..., j] for j, name in enumerate(_METRIC_NAMES)}
         return AnakinExperimentOutput(learner_state=learner_state, episode_metrics=ep_out, train_metrics=train_metrics)
 
     learner_fn.built = built  # exposed for tests / bench (trajectory buffers, graph handle)
     learner_fn.update_step = _update_step
-    learner_fn.phases = {"rollout": _rollout_phase, "gae": _gae_phase, "update": _update_phase, "carry": _carry_phase}
-    learner_fn.ensure_built = lambda st: (_build(st), [built["shards"][u].obs[0].copy_(st.timestep[u].observation) for u in range(U)]) if not built else None
+    learner_fn.phases = {"rollout": _rollout_phase, "gae": _gae_phase, "update": _update_phase}
+
+    def _ensure_built(st: OnPolicyLearnerState) -> None:
+        if not built:
+            _build(st)
+            for u in range(U):  # last_timestep.observation seeds the carry slot (row T)
+                built["shards"][u].obs[T].copy_(st.timestep[u].observation)
+
+    learner_fn.ensure_built = _ensure_built
     return learner_fn
 
 

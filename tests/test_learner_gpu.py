@@ -87,7 +87,7 @@ def test_update_step_matches_oracle(E, T, nmb, layers, obs_dim, A, graph):
         np.testing.assert_allclose(_np(state.params.actor_params.flat), actor.flat(), rtol=1e-4, atol=2e-6)
         np.testing.assert_allclose(_np(state.params.critic_params.flat), critic.flat(), rtol=1e-4, atol=2e-6)
         # the carried observation is the env's latest one (ff_ppo.py:131-134)
-        assert torch.equal(learn.built["shards"][0].obs[0], learn.built["shards"][0].obs[T])
+        assert torch.equal(state.timestep[0].observation, learn.built["shards"][0].obs[T])
     counts = state.params.actor_params.arena_counts.cpu().tolist()
     assert counts == [n_updates * 4 * nmb] * 4
     assert out.episode_metrics["episode_return"].shape == (1, 1, T, E)
