@@ -27,6 +27,11 @@ def _np(t):
     return t.detach().float().cpu().numpy().astype(np.float64)
 
 
+def adv_raw(traj):
+    r_t, d_t, tr = O.ppo_gae_inputs(traj.reward, traj.done, traj.truncated, 0.99, 1.0)
+    return O.gae(r_t, d_t, 0.95, v_tm1=traj.value, v_t=traj.bootstrap_value, truncation_t=tr, time_major=True)[0]
+
+
 def _tree_to_oracle(tree):
     spec = tree.spec
     return O.MLPParams.from_flat(_np(tree.flat), list(spec.sizes))
@@ -79,9 +84,7 @@ def test_update_step_matches_oracle(E, T, nmb, layers, obs_dim, A, graph):
         ])
         actor, critic, metrics, adv, tgt = O.ppo_update(actor, critic, a_st, c_st, traj, perms, h)
         np.testing.assert_allclose(_np(sh.targets), tgt, rtol=1e-4, atol=2e-5)
-        np.testing.assert_allclose(_np(sh.advantages), O.gae(*O.ppo_gae_inputs(traj.reward, traj.done, traj.truncated, 0.99, 1.0), 0.95,
-                                   v_tm1=traj.value, v_t=traj.bootstrap_value, truncation_t=traj.truncated.astype(np.float64), time_major=True)[0],
-                                   rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(_np(sh.advantages), adv_raw(traj), rtol=1e-4, atol=2e-5)  # raw: standardised on load
         for name in ("actor_loss", "entropy", "value_loss"):
             np.testing.assert_allclose(_np(out.train_metrics[name][0]), metrics[name], rtol=2e-4, atol=2e-6)
         np.testing.assert_allclose(_np(state.params.actor_params.flat), actor.flat(), rtol=1e-4, atol=2e-6)
