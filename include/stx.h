@@ -67,7 +67,7 @@ typedef struct StxPpoHyper {
 /* One optimiser = optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps=1e-5))
  * (ff_ppo.py:449-463) over one contiguous segment of the flat arenas. */
 typedef struct StxAdamSeg {
-  int64_t offset;      /* first float of the segment in the arenas (multiple of 4) */
+  int64_t offset;      /* first float of the segment in the arenas (multiple of 4; stx_ppo_arena_offsets gives 8) */
   int64_t count;       /* floats in the segment (padding excluded or zero-filled) */
   float init_lr;       /* system.actor_lr / critic_lr */
   float max_grad_norm; /* system.max_grad_norm */
@@ -129,6 +129,11 @@ int stx_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t
                     int64_t M, float* out, int precision, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Bring-up / test hook of the bf16 tensor-core forward: as stx_mlp_forward(STX_PREC_BF16) and also
+ * writes the bf16-rounded hidden activations h1, h2 ((M, 256) f32 each, nullable). */
+int stx_tc_debug_forward(const StxMlp* mlp, const void* x, int64_t ldx, int64_t M, float* out, float* h1,
+                         float* h2, void* stream);
+
 /* Categorical head ops on logits (E, A) -- tfd.Categorical (stoix/networks/heads.py:41) as used at
  * ff_ppo.py:100-101.  If sample != 0: action = argmax_j(logits_j + Gumbel_j) with Philox4x32-10
  * keyed by seed with counter (row, call = offset + *dev_counter); else `action` is an input.
@@ -144,7 +149,7 @@ int stx_categorical(const float* logits, int64_t E, int A, int sample, uint64_t 
  * ppo_clip_loss / clipped_value_loss (stoix/utils/loss.py:17-32, 68-78).  For minibatch rows
  * idx = perm[mb_off : mb_off+mb] of the flat (T*E) batch it re-runs both networks on obs[idx],
  * evaluates the two losses and ACCUMULATES d(total_loss)/d(params) into grad_arena (caller zeroes
- * it; layout = [actor arena | pad to 4 | critic arena], see stx_ppo_arena_offsets).
+ * it; layout = [actor arena | pad to 8 | critic arena | pad to 8], see stx_ppo_arena_offsets).
  * metrics[6] += {actor_loss, entropy, value_loss, mean(adv used), mean(pred value), mean(target)}.
  * obs: (B, D) f32 or bf16 per `precision`; perm NULL -> identity.
  */

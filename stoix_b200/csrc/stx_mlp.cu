@@ -257,10 +257,10 @@ extern "C" int stx_categorical(const float* logits, int64_t E, int A, int sample
 extern "C" void stx_ppo_arena_offsets(const StxMlp* actor, const StxMlp* critic, int64_t* actor_off,
                                       int64_t* critic_off, int64_t* total) {
   const int64_t na = stx_mlp_param_count(actor), nc = stx_mlp_param_count(critic);
-  const int64_t coff = (na + 3) / 4 * 4;
+  const int64_t coff = (na + 7) / 8 * 8;  // 8 floats: the bf16 shadow of each network stays 16-byte aligned (TMA)
   if (actor_off) *actor_off = 0;
   if (critic_off) *critic_off = coff;
-  if (total) *total = coff + (nc + 3) / 4 * 4;
+  if (total) *total = coff + (nc + 7) / 8 * 8;
 }
 
 extern "C" size_t stx_ppo_workspace_bytes(const StxMlp* actor, const StxMlp* critic, int64_t mb, int precision) {

@@ -86,9 +86,10 @@ class MlpSpec:
 
 
 def arena_offsets(actor: MlpSpec, critic: MlpSpec) -> Tuple[int, int, int]:
-    """[actor | pad to 4 floats | critic | pad] -- mirrors stx_ppo_arena_offsets."""
-    coff = (actor.param_count + 3) // 4 * 4
-    return 0, coff, coff + (critic.param_count + 3) // 4 * 4
+    """[actor | pad to 8 floats | critic | pad] -- mirrors stx_ppo_arena_offsets (8 floats keeps the bf16
+    shadow of each network 16-byte aligned for TMA)."""
+    coff = (actor.param_count + 7) // 8 * 8
+    return 0, coff, coff + (critic.param_count + 7) // 8 * 8
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,6 +174,19 @@ def mlp_forward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, row_idx: O
         "stx_mlp_forward",
     )
     return out
+
+
+def tc_debug_forward(spec: MlpSpec, params: torch.Tensor, params_bf16: torch.Tensor, x: torch.Tensor):
+    """bf16 tensor-core forward returning (out, h1, h2) -- test hook."""
+    dev = _need_cuda(params, params_bf16, x)
+    M = x.shape[0]
+    out = torch.empty((M, spec.sizes[-1]), dtype=torch.float32, device=dev)
+    h1 = torch.empty((M, 256), dtype=torch.float32, device=dev)
+    h2 = torch.empty((M, 256), dtype=torch.float32, device=dev)
+    m = spec.c_struct(params, params_bf16)
+    _lib.check(_lib.load().stx_tc_debug_forward(C.byref(m), _p(x), x.stride(0), M, _p(out), _p(h1), _p(h2), _stream()),
+               "stx_tc_debug_forward")
+    return out, h1, h2
 
 
 def categorical(logits: torch.Tensor, action: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,

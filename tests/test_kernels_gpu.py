@@ -169,8 +169,8 @@ def test_clip_adam_vs_oracle(grad_mag, decay):
 
     rng = np.random.default_rng(1)
     na, nc = 84488, 82689
-    coff = (na + 3) // 4 * 4
-    total = coff + (nc + 3) // 4 * 4
+    coff = (na + 7) // 8 * 8
+    total = coff + (nc + 7) // 8 * 8
     p0 = np.zeros(total, np.float32)
     p0[:na] = rng.standard_normal(na) * 0.1
     p0[coff : coff + nc] = rng.standard_normal(nc) * 0.1
