@@ -257,6 +257,11 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
   return STX_OK;
 }
 
+int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
+                    uint32_t box_cols) {
+  return make_map_2d(m, base, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 static bool tc_shape_ok(const StxMlp* m) {
   return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
          m->sizes[3] >= 1 && m->sizes[3] <= 16;
@@ -301,13 +306,6 @@ int tc_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t*
                    cudaStream_t st) {
   STX_REQUIRE(row_idx == nullptr, STX_E_UNSUPPORTED, "STX_PREC_BF16 stx_mlp_forward does not take a row gather");
   return tc::tc_forward_impl(mlp, x, ldx, M, out, nullptr, nullptr, st);
-}
-
-size_t tc_ppo_workspace_bytes(const StxMlp*, const StxMlp*, int64_t) { return 256; }
-int tc_ppo_minibatch_grads(const StxMlp*, const StxMlp*, const StxPpoBatch*, int64_t, int64_t, const StxPpoHyper*, float, float*,
-                           float*, void*, size_t, cudaStream_t) {
-  set_error("STX_PREC_BF16 PPO update is not built into this library yet");
-  return STX_E_UNSUPPORTED;
 }
 
 }  // namespace stx

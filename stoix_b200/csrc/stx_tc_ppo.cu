@@ -1,0 +1,735 @@
+// K3 (bf16 path): the PPO minibatch gradient step on tcgen05 tensor cores.
+//
+// Reference semantics: _actor_loss_fn / _critic_loss_fn + jax.grad for one minibatch
+// (stoix/systems/ppo/anakin/ff_ppo.py:184-247; losses stoix/utils/loss.py:17-32,68-78).  Three launches:
+//
+//  tc_ppo_fwd_bwd_kernel (K3a)  one persistent CTA per SM; CTAs [0, n_a) run the actor, the rest the critic.
+//      Per 128-row tile (rows gathered through the shuffle permutation straight into 128B-swizzled smem):
+//        G0 X*W0 -> E0 h1=relu(.+b0) -> G1 h1*W1 -> E1 h2 -> G2 h2*W2 -> E2 loss + d(logits|value) ->
+//        G3 dz*W2^T -> E3 dh2 = .*(h2>0) -> G4 dh2*W1^T -> E4 dh1 = .*(h1>0)
+//      All five GEMMs run on tcgen05 with the hidden activations resident in tensor memory (A operand
+//      from TMEM); W1's single smem image serves as MN-major B (forward) and K-major B (backward).
+//      Epilogue warps also emit h1, h2, dh2, dh1, dz (bf16) for the weight-gradient GEMMs, reduce the
+//      bias gradients with a shuffle butterfly and accumulate the loss metrics.
+//  tc_dw_kernel (K3b)  split-K GEMMs dW = A^T * B over the minibatch rows with both operands MN-major
+//      (TMA 64-column blocks, 3-stage mbarrier pipeline), 256 x N fp32 accumulators in TMEM:
+//        dW1 = h1^T dh2 (N=256), dW2 = h2^T dz (N=64 padded), dW0^T = dh1^T x (N=64 padded).
+//  tc_reduce_kernel     fixed-order reduction of the per-CTA partials into the flat fp32 gradient arena
+//      (deterministic; also the bias gradients and the six loss metrics).
+#include <cuda.h>
+
+#include "stx_common.cuh"
+#include "stx_tc_ptx.cuh"
+
+namespace stx {
+namespace tc {
+
+int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
+                    uint32_t box_cols);  // stx_tc_mlp.cu (SWIZZLE_128B bf16)
+
+constexpr int kTileM = 128;
+constexpr int kH = 256;
+constexpr int kFbThreads = 320;  // warp 0 gather producer, warp 1 MMA, warps 2..9 epilogue
+
+// ---- K3a shared-memory map ------------------------------------------------------------------------
+constexpr uint32_t kOffW1 = 0;
+constexpr uint32_t kOffW0 = 131072;
+constexpr uint32_t kOffW2 = 163840;
+constexpr uint32_t kOffX = 172032;                 // 2 stages x 16 KB
+constexpr uint32_t kOffDz = kOffX + 2 * 16384;     // 4 KB: dz tile, K-major core matrices
+constexpr uint32_t kOffBias = kOffDz + 4096;       // b0[256] b1[256] b2[16]
+constexpr uint32_t kOffDb = kOffBias + 528 * 4;    // [4 lane quarters][db0[256] db1[256] db2[16]] accumulators
+constexpr uint32_t kOffBar = kOffDb + 4 * 528 * 4;
+constexpr uint32_t kFbSmemBytes = kOffBar + 128 + 1024;
+
+struct FbNet {
+  const __nv_bfloat16* w2;   // [256 x A] bf16
+  const float *b0, *b1, *b2;
+  __nv_bfloat16 *h1, *h2, *dh1, *dh2;  // [mb x 256]
+  __nv_bfloat16* dz;                   // [mb x 64] (columns >= A stay zero)
+  float* db_part;                      // [n_cta_of_net][528]
+  int A;
+  int is_actor;
+};
+
+struct FbParams {
+  FbNet net[2];
+  int n_cta[2];             // CTAs per net (actor first)
+  const __nv_bfloat16* obs; // [B x D]
+  __nv_bfloat16* xg;        // [mb x 64] gathered input rows (written by the actor CTAs)
+  const int32_t* idx;       // perm + mb_off, or nullptr (then rows are row0 + i)
+  int64_t row0;
+  const int32_t* action;
+  const float *logp_old, *v_old, *adv, *tgt, *adv_stats;
+  float* metric_part;       // [gridDim][8]
+  int D;
+  int mb;
+  float clip_eps, ent_coef, vf_coef;
+};
+
+// sum over the 32 lanes of a warp of v[i], i = 0..31: afterwards v[0] of lane l holds the total of
+// column l (reduce-scatter butterfly: 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const bool hi = (lane & s) != 0;
+      const float send = hi ? v[i] : v[i + s];
+      const float keep = hi ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kFbThreads, 1)
+    tc_ppo_fwd_bwd_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
+                          const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
+                          const FbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  float* s_b0 = reinterpret_cast<float*>(smem + kOffBias);
+  float* s_b1 = s_b0 + 256;
+  float* s_b2 = s_b1 + 256;
+  float* s_db = reinterpret_cast<float*>(smem + kOffDb);  // [4][528]: one slice per lane quarter -> no atomics, fixed order
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* x_full = bars;       // [2]
+  uint64_t* x_empty = bars + 2;  // [2]
+  uint64_t* w_full = bars + 4;
+  uint64_t* mma_done = bars + 5;
+  uint64_t* epi_done = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int which = (int)blockIdx.x < p.n_cta[0] ? 0 : 1;
+  const FbNet& net = p.net[which];
+  const int cta_in_net = which == 0 ? (int)blockIdx.x : (int)blockIdx.x - p.n_cta[0];
+  const int ncta = p.n_cta[which];
+  const int num_tiles = p.mb / kTileM;
+  const int my_tiles = cta_in_net < num_tiles ? (num_tiles - cta_in_net + ncta - 1) / ncta : 0;
+  const CUtensorMap* tmW0 = which == 0 ? &tmW0a : &tmW0c;
+  const CUtensorMap* tmW1 = which == 0 ? &tmW1a : &tmW1c;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(epi_done, 8);
+    fence_barrier_init();
+    tma_prefetch_desc(tmW0);
+    tma_prefetch_desc(tmW1);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  {
+    __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(smem + kOffW2);
+    for (int i = threadIdx.x; i < kH * 16; i += kFbThreads) {
+      const int j = i >> 4, n = i & 15;
+      const __nv_bfloat16 v = n < net.A ? net.w2[j * net.A + n] : __float2bfloat16_rn(0.f);
+      w2s[((j >> 3) * 256 + (n >> 3) * 128 + (j & 7) * 16 + (n & 7) * 2) >> 1] = v;
+    }
+    for (int i = threadIdx.x; i < 256; i += kFbThreads) s_b0[i] = net.b0[i], s_b1[i] = net.b1[i];
+    if (threadIdx.x < 16) s_b2[threadIdx.x] = threadIdx.x < net.A ? net.b2[threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < 4 * 528; i += kFbThreads) s_db[i] = 0.f;
+    fence_async_proxy();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  float m_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actor_loss, entropy, value_loss, adv, pred value, target
+
+  if (warp == 0) {
+    // ===================== producer: weights by TMA, X rows by gather =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 32768 + 131072);
+      for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
+      for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
+    }
+    const int dchunks = p.D >> 3;  // 16-byte chunks per observation row
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
+      if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) & 1) ^ 1, 1);
+      const int tile = cta_in_net + it * ncta;
+      uint8_t* xs = smem + kOffX + s * 16384;
+#pragma unroll 4
+      for (int e = lane; e < kTileM * 8; e += 32) {
+        const int r = e >> 3, c = e & 7;
+        const int64_t mrow = (int64_t)tile * kTileM + r;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c < dchunks) {
+          const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+          v = *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8);
+        }
+        *reinterpret_cast<uint4*>(xs + r * 128 + ((c ^ (r & 7)) << 4)) = v;  // Swizzle<3,4,3>
+        if (which == 0) *reinterpret_cast<uint4*>(p.xg + mrow * 64 + c * 8) = v;
+      }
+      fence_async_proxy();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_full[s]);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_fwd = idesc_bf16(128, 256, 0, 1);   // B = W (in,out) image as MN-major
+    constexpr uint32_t idesc_head = idesc_bf16(128, 16, 0, 1);
+    constexpr uint32_t idesc_bwd = idesc_bf16(128, 256, 0, 0);   // B = same images read as K-major
+    const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
+    mbar_wait(w_full, 0, 2);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
+      const int g0 = 5 * it;
+      mbar_wait(&x_full[s], (it >> 1) & 1, 3);
+      if (g0 > 0) mbar_wait(epi_done, (g0 - 1) & 1, 4);
+      tc_fence_after();
+      if (elect_one()) {  // G0: D = X * W0
+        const uint32_t xa = sbase + kOffX + s * 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_ss(tmem_d, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
+                 smem_desc(sbase + kOffW0 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+        mma_commit(&x_empty[s]);
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+      mbar_wait(epi_done, g0 & 1, 5);
+      tc_fence_after();
+      if (elect_one()) {  // G1: D = h1 * W1
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          mma_ts(tmem_d, tmem_a1 + k * 8, smem_desc(sbase + kOffW1 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+      mbar_wait(epi_done, (g0 + 1) & 1, 6);
+      tc_fence_after();
+      if (elect_one()) {  // G2: D[:, :16] = h2 * W2
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_head, k > 0);
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+      mbar_wait(epi_done, (g0 + 2) & 1, 7);
+      tc_fence_after();
+      if (elect_one()) {  // G3: D = dz (smem, K-major core matrices) * W2^T (same W2 image, K-major)
+        mma_ss(tmem_d, smem_desc(sbase + kOffDz, 128, 256, SWIZZLE_NONE), smem_desc(sbase + kOffW2, 128, 256, SWIZZLE_NONE),
+               idesc_bwd, 0);
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+      mbar_wait(epi_done, (g0 + 3) & 1, 8);
+      tc_fence_after();
+      if (elect_one()) {  // G4: D = dh2 * W1^T  (W1 image as K-major SW128: 4 K-blocks of 64)
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW1 + (k >> 2) * 32768 + (k & 3) * 32, 16, 1024, SWIZZLE_128B),
+                 idesc_bwd, k > 0);
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue warps 2..9: lane quarter q, column half `half` =====================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
+    const float inv_m = 1.0f / (float)p.mb;
+    float adv_mean = 0.f, adv_rstd = 1.f;
+    if (p.adv_stats) adv_mean = p.adv_stats[0], adv_rstd = p.adv_stats[1];
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = cta_in_net + it * ncta;
+      const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
+      const int g0 = 5 * it;
+      // ---------------- E0 / E1: hidden layers ----------------
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        mbar_wait(mma_done, (g0 + layer) & 1, 10 + layer);
+        tc_fence_after();
+        const float* bias = layer == 0 ? s_b0 : s_b1;
+        const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
+        __nv_bfloat16* hout = (layer == 0 ? net.h1 : net.h2) + mrow * kH;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half * 4 + cc;
+          uint32_t r[32], pk[16];
+          tmem_ld32(tmem_d + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
+            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
+            pk[j] = pack_bf16(v0, v1);
+          }
+          tmem_st16(ta + c * 16, pk);
+          uint4* dst = reinterpret_cast<uint4*>(hout + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(epi_done);
+      }
+      // ---------------- E2: head + loss + d(head) ----------------
+      mbar_wait(mma_done, (g0 + 2) & 1, 12);
+      tc_fence_after();
+      if (half == 0) {
+        uint32_t r[16];
+        tmem_ld16(tmem_d, r);
+        tmem_ld_wait();
+        const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+        float dz[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dz[j] = 0.f;
+        if (net.is_actor) {
+          const int A = net.A;
+          float z[16], zmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            z[j] = __uint_as_float(r[j]) + s_b2[j];
+            if (j < A) zmax = fmaxf(zmax, z[j]);
+          }
+          float se = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < A) se += expf(z[j] - zmax);
+          const float lse = zmax + logf(se);
+          const int a = p.action[src];
+          const float adv = (p.adv[src] - adv_mean) * adv_rstd;
+          float ent = 0.f, logp_a = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < A) {
+              const float lp = z[j] - lse;
+              ent -= expf(lp) * lp;
+              if (j == a) logp_a = lp;
+            }
+          const float ratio = expf(logp_a - p.logp_old[src]);
+          const float l1 = ratio * adv;
+          const float l2 = fminf(fmaxf(ratio, 1.0f - p.clip_eps), 1.0f + p.clip_eps) * adv;
+          const bool in_band = (ratio >= 1.0f - p.clip_eps) && (ratio <= 1.0f + p.clip_eps);
+          const float dlogp = ((l1 < l2) || in_band) ? -adv * ratio * inv_m : 0.f;
+          const float ce = p.ent_coef * inv_m;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < A) {
+              const float lp = z[j] - lse, pr = expf(lp);
+              dz[j] = dlogp * ((j == a ? 1.f : 0.f) - pr) + ce * pr * (lp + ent);
+            }
+          m_acc[0] += -fminf(l1, l2), m_acc[1] += ent, m_acc[3] += adv;
+        } else {
+          const float v = __uint_as_float(r[0]) + s_b2[0], vo = p.v_old[src], tg = p.tgt[src];
+          const float diff = v - vo;
+          const float vclip = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
+          const float e1 = v - tg, e2 = vclip - tg, q1 = e1 * e1, q2 = e2 * e2;
+          const float g2 = (fabsf(diff) < p.clip_eps) ? e2 : 0.f;
+          const float dv = q1 > q2 ? e1 : (q1 < q2 ? g2 : 0.5f * (e1 + g2));
+          dz[0] = p.vf_coef * dv * inv_m;
+          m_acc[2] += 0.5f * fmaxf(q1, q2), m_acc[4] += v, m_acc[5] += tg;
+        }
+        // bias gradient of the head: column sums over the 32 rows of this warp (16 columns)
+        {
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = dz[j], t[16 + j] = 0.f;
+          const float cs = warp_colsum32(t, lane);
+          if (lane < 16) s_db[q * 528 + 512 + lane] += cs;
+        }
+        // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(dz[2 * j], dz[2 * j + 1]);
+        const int mr = q * 32 + lane;
+        uint8_t* dzs = smem + kOffDz + (mr >> 3) * 256 + (mr & 7) * 16;
+        *reinterpret_cast<uint4*>(dzs) = make_uint4(pk[0], pk[1], pk[2], pk[3]);        // k = 0..7
+        *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
+        uint4* gz = reinterpret_cast<uint4*>(net.dz + mrow * 64);
+        gz[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        gz[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        fence_async_proxy();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      // ---------------- E3 / E4: dh2 = D * (h2 > 0) ; dh1 = D * (h1 > 0) ----------------
+#pragma unroll 1
+      for (int layer = 1; layer >= 0; --layer) {
+        mbar_wait(mma_done, (g0 + 3 + (1 - layer)) & 1, 13 + layer);
+        tc_fence_after();
+        const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
+        __nv_bfloat16* dout = (layer == 1 ? net.dh2 : net.dh1) + mrow * kH;
+        float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half * 4 + cc;
+          uint32_t r[32], hm[16], pk[16];
+          tmem_ld32(tmem_d + c * 32, r);
+          tmem_ld16(ta + c * 16, hm);
+          tmem_ld_wait();
+          float dv[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // h is post-relu (>= 0): positive <=> bf16 bit pattern non-zero (and not -0)
+            const bool p0 = (hm[j] & 0x7FFFu) != 0u, p1 = (hm[j] & 0x7FFF0000u) != 0u;
+            dv[2 * j] = p0 ? __uint_as_float(r[2 * j]) : 0.f;
+            dv[2 * j + 1] = p1 ? __uint_as_float(r[2 * j + 1]) : 0.f;
+            pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
+          }
+          if (layer == 1) tmem_st16(ta + c * 16, pk);  // dh2 replaces h2 as the A operand of G4
+          uint4* dst = reinterpret_cast<uint4*>(dout + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          const float cs = warp_colsum32(dv, lane);
+          dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
+        }
+        if (layer == 1) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(epi_done);
+      }
+    }
+  }
+  // ---- teardown: bias-gradient and metric partials of this CTA ----
+  tc_fence_before();
+  __syncthreads();
+  for (int i = threadIdx.x; i < 528; i += kFbThreads)
+    net.db_part[(int64_t)cta_in_net * 528 + i] = (s_db[i] + s_db[528 + i]) + (s_db[2 * 528 + i] + s_db[3 * 528 + i]);
+  {
+    __shared__ float s_mw[kFbThreads / 32][6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float w = warp_sum(m_acc[k]);
+      if (lane == 0) s_mw[warp][k] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float acc = 0.f;
+      if (threadIdx.x < 6)
+        for (int w = 0; w < kFbThreads / 32; ++w) acc += s_mw[w][threadIdx.x];
+      p.metric_part[(int64_t)blockIdx.x * 8 + threadIdx.x] = acc;
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================== K3b: dW = A^T * B ===============================================
+constexpr int kDwThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kDwStages = 3;
+constexpr uint32_t kDwStageBytes = 65536;  // A [64 x 256] 32 KB + B [64 x <=256] 32 KB
+constexpr uint32_t kDwOffBar = kDwStages * kDwStageBytes;
+constexpr uint32_t kDwSmemBytes = kDwOffBar + 128 + 1024;
+constexpr int kMaxJobs = 6;
+
+struct DwJob {
+  float* part;     // [n_cta][256 x N] fp32 partial outputs
+  int N;           // 64 or 256
+  int cta_begin;   // first CTA of this job
+  int n_cta;
+  int num_chunks;  // mb / 64
+};
+struct DwParams {
+  DwJob job[kMaxJobs];
+  int n_jobs;
+};
+struct DwMaps {
+  CUtensorMap a[kMaxJobs];  // [mb x 256] bf16, box 64 rows x 64 cols
+  CUtensorMap b[kMaxJobs];  // [mb x N]
+};
+
+__global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwOffBar);
+  uint64_t* full = bars;                 // [kDwStages]
+  uint64_t* empty = bars + kDwStages;    // [kDwStages]
+  uint64_t* acc_done = bars + 2 * kDwStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDwStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int j = 0;
+  while (j + 1 < p.n_jobs && (int)blockIdx.x >= p.job[j + 1].cta_begin) ++j;
+  const DwJob& job = p.job[j];
+  const int cta = (int)blockIdx.x - job.cta_begin;
+  const int my_chunks = cta < job.num_chunks ? (job.num_chunks - cta + job.n_cta - 1) / job.n_cta : 0;
+  const int nblk = job.N >> 6;
+  const uint32_t stage_tx = 32768 + (uint32_t)job.N * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.a[j]);
+    tma_prefetch_desc(&maps.b[j]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < my_chunks; ++it) {
+        const int s = it % kDwStages;
+        if (it >= kDwStages) mbar_wait(&empty[s], ((it / kDwStages) & 1) ^ 1, 20);
+        const int row = (cta + it * job.n_cta) * 64;
+        uint8_t* st = smem + s * kDwStageBytes;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 8192, &maps.a[j], &full[s], b * 64, row);
+        for (int b = 0; b < nblk; ++b) tma_load_2d(st + 32768 + b * 8192, &maps.b[j], &full[s], b * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_bf16(128, job.N, 1, 1);  // both operands MN-major
+    for (int it = 0; it < my_chunks; ++it) {
+      const int s = it % kDwStages;
+      mbar_wait(&full[s], (it / kDwStages) & 1, 21);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = sbase + s * kDwStageBytes, b0 = a0 + 32768;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {      // 16 rows (K) per step = two 8-row groups of 1024 B
+#pragma unroll
+          for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128)
+            mma_ss(tmem + h * 256, smem_desc(a0 + h * 16384 + k * 2048, 8192, 1024, SWIZZLE_128B),
+                   smem_desc(b0 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(acc_done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* out = job.part + (int64_t)cta * 256 * job.N;
+    if (my_chunks > 0) {
+      mbar_wait(acc_done, 0, 22);
+      tc_fence_after();
+    }
+    for (int h = 0; h < 2; ++h) {
+      float* orow = out + (int64_t)(h * 128 + q * 32 + lane) * job.N;
+      for (int c = 0; c < job.N / 32; ++c) {
+        uint32_t r[32];
+        if (my_chunks > 0) {
+          tmem_ld32(tmem + lane_addr + h * 256 + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================== reduce partials -> gradient arena ================================
+struct RedSeg {
+  const float* part;   // partial base
+  int64_t part_stride; // floats between CTAs' partials
+  int n_part;
+  int rows, cols;      // destination matrix (rows x cols) at grad + dst_off, row-major
+  int src_ld;          // leading dimension of one partial
+  int transpose;       // 1: dst[r][c] = src[c][r]
+  int64_t dst_off;
+};
+struct RedParams {
+  RedSeg seg[12];
+  int n_seg;
+  const float* metric_part;  // [n_cta_total][8]
+  int n_cta_total;
+  float* metrics;            // [6] accumulated
+  float weight;
+  float inv_mb;
+};
+
+__global__ void tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
+  for (int s = 0; s < p.n_seg; ++s) {
+    const RedSeg& g = p.seg[s];
+    const int64_t n = (int64_t)g.rows * g.cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / g.cols), c = (int)(i % g.cols);
+      const int64_t so = g.transpose ? (int64_t)c * g.src_ld + r : (int64_t)r * g.src_ld + c;
+      float acc = 0.f;
+      for (int k = 0; k < g.n_part; ++k) acc += g.part[(int64_t)k * g.part_stride + so];
+      grad[g.dst_off + i] += p.weight * acc;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 6) {
+    float acc = 0.f;
+    for (int k = 0; k < p.n_cta_total; ++k) acc += p.metric_part[(int64_t)k * 8 + threadIdx.x];
+    p.metrics[threadIdx.x] += p.weight * acc * p.inv_mb;
+  }
+}
+
+// =============================== host side =======================================================
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+struct TcWs {
+  __nv_bfloat16 *h1[2], *h2[2], *dh1[2], *dh2[2], *dz[2], *xg;
+  float *part_w1[2], *part_w2[2], *part_w0[2], *db_part[2], *metric_part;
+  size_t bytes;
+};
+
+constexpr int kCtaPerNet = kNumSMs / 2;              // 74
+constexpr int kDwCtaW1 = 38, kDwCtaW2 = 18, kDwCtaW0 = 18;  // per net: 74
+
+TcWs carve_tc(int64_t mb, char* base) {
+  TcWs w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    char* q = base ? base + o : nullptr;
+    o += al(bytes);
+    return q;
+  };
+  for (int n = 0; n < 2; ++n) {
+    w.h1[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
+    w.h2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
+    w.dh1[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
+    w.dh2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
+    w.dz[n] = (__nv_bfloat16*)take((size_t)mb * 64 * 2);
+    w.part_w1[n] = (float*)take((size_t)kDwCtaW1 * 65536 * 4);
+    w.part_w2[n] = (float*)take((size_t)kDwCtaW2 * 256 * 64 * 4);
+    w.part_w0[n] = (float*)take((size_t)kDwCtaW0 * 256 * 64 * 4);
+    w.db_part[n] = (float*)take((size_t)kCtaPerNet * 528 * 4);
+  }
+  w.xg = (__nv_bfloat16*)take((size_t)mb * 64 * 2);
+  w.metric_part = (float*)take((size_t)kNumSMs * 8 * 4);
+  w.bytes = o;
+  return w;
+}
+
+bool tc_ppo_shape_ok(const StxMlp* m) {
+  return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
+         m->sizes[3] >= 1 && m->sizes[3] <= 16;
+}
+
+}  // namespace tc
+
+size_t tc_ppo_workspace_bytes(const StxMlp* a, const StxMlp* c, int64_t mb) {
+  (void)a, (void)c;
+  return tc::carve_tc(mb, nullptr).bytes;
+}
+
+int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* b, int64_t mb_off, int64_t mb,
+                           const StxPpoHyper* h, float grad_weight, float* grad_arena, float* metrics, void* ws_raw, size_t,
+                           cudaStream_t st) {
+  using namespace tc;
+  STX_REQUIRE(tc_ppo_shape_ok(actor) && tc_ppo_shape_ok(critic), STX_E_SHAPE,
+              "STX_PREC_BF16 PPO kernels need MLP [D<=64 (mult of 8), 256, 256, head<=16]");
+  STX_REQUIRE(mb % 128 == 0, STX_E_SHAPE, "STX_PREC_BF16 PPO kernels need a minibatch that is a multiple of 128 rows (got %lld)", (long long)mb);
+  STX_REQUIRE(actor->params_bf16 && critic->params_bf16, STX_E_ARG, "STX_PREC_BF16 needs the bf16 shadow arenas");
+  const int D = actor->sizes[0];
+  const StxMlp* nets[2] = {actor, critic};
+  TcWs ws = carve_tc(mb, reinterpret_cast<char*>(ws_raw));
+  int64_t aoff, coff, total;
+  stx_ppo_arena_offsets(actor, critic, &aoff, &coff, &total);
+  const int64_t noff[2] = {aoff, coff};
+
+  // ---- K3a ----
+  FbParams fp{};
+  CUtensorMap tmW0[2], tmW1[2];
+  for (int n = 0; n < 2; ++n) {
+    const StxMlp* m = nets[n];
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(m->params_bf16);
+    const int A = m->sizes[3];
+    const int64_t off_w1 = (int64_t)D * kH + kH, off_w2 = off_w1 + (int64_t)kH * kH + kH;
+    if (int rc = make_map_2d_pub(&tmW0[n], w, (uint64_t)D, kH, kH, 64, 64)) return rc;
+    if (int rc = make_map_2d_pub(&tmW1[n], w + off_w1, kH, kH, kH, 256, 64)) return rc;
+    FbNet& fn = fp.net[n];
+    fn.w2 = w + off_w2;
+    fn.b0 = m->params + (int64_t)D * kH, fn.b1 = m->params + off_w1 + (int64_t)kH * kH, fn.b2 = m->params + off_w2 + (int64_t)kH * A;
+    fn.h1 = ws.h1[n], fn.h2 = ws.h2[n], fn.dh1 = ws.dh1[n], fn.dh2 = ws.dh2[n], fn.dz = ws.dz[n];
+    fn.db_part = ws.db_part[n], fn.A = A, fn.is_actor = (n == 0);
+    fp.n_cta[n] = kCtaPerNet;
+  }
+  fp.obs = reinterpret_cast<const __nv_bfloat16*>(b->obs);
+  fp.xg = ws.xg;
+  fp.idx = b->perm ? b->perm + mb_off : nullptr;
+  fp.row0 = mb_off;
+  fp.action = b->action, fp.logp_old = b->log_prob, fp.v_old = b->value, fp.adv = b->advantages, fp.tgt = b->targets;
+  fp.adv_stats = h->standardize_advantages ? b->adv_stats : nullptr;
+  fp.metric_part = ws.metric_part;
+  fp.D = D, fp.mb = (int)mb, fp.clip_eps = h->clip_eps, fp.ent_coef = h->ent_coef, fp.vf_coef = h->vf_coef;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STX_CUDA_OK(cudaFuncSetAttribute(tc_ppo_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbSmemBytes));
+    STX_CUDA_OK(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
+    attr_set = true;
+  }
+  tc_ppo_fwd_bwd_kernel<<<2 * kCtaPerNet, kFbThreads, kFbSmemBytes, st>>>(tmW0[0], tmW1[0], tmW0[1], tmW1[1], fp);
+  STX_LAUNCH_OK();
+
+  // ---- K3b ----
+  DwMaps maps;
+  DwParams dp{};
+  int cta = 0, jn = 0;
+  const int chunks = (int)(mb / 64);
+  for (int n = 0; n < 2; ++n) {
+    // dW1 = h1^T dh2
+    if (int rc = make_map_2d_pub(&maps.a[jn], ws.h1[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
+    if (int rc = make_map_2d_pub(&maps.b[jn], ws.dh2[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
+    dp.job[jn] = DwJob{ws.part_w1[n], 256, cta, kDwCtaW1, chunks};
+    cta += kDwCtaW1, ++jn;
+    // dW2 = h2^T dz(padded to 64)
+    if (int rc = make_map_2d_pub(&maps.a[jn], ws.h2[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
+    if (int rc = make_map_2d_pub(&maps.b[jn], ws.dz[n], (uint64_t)mb, 64, 64, 64, 64)) return rc;
+    dp.job[jn] = DwJob{ws.part_w2[n], 64, cta, kDwCtaW2, chunks};
+    cta += kDwCtaW2, ++jn;
+    // dW0^T = dh1^T x(padded to 64)
+    if (int rc = make_map_2d_pub(&maps.a[jn], ws.dh1[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
+    if (int rc = make_map_2d_pub(&maps.b[jn], ws.xg, (uint64_t)mb, 64, 64, 64, 64)) return rc;
+    dp.job[jn] = DwJob{ws.part_w0[n], 64, cta, kDwCtaW0, chunks};
+    cta += kDwCtaW0, ++jn;
+  }
+  dp.n_jobs = jn;
+  tc_dw_kernel<<<cta, kDwThreads, kDwSmemBytes, st>>>(maps, dp);
+  STX_LAUNCH_OK();
+
+  // ---- reduce ----
+  RedParams rp{};
+  int sidx = 0;
+  for (int n = 0; n < 2; ++n) {
+    const int A = nets[n]->sizes[3];
+    const int64_t o_w0 = noff[n], o_b0 = o_w0 + (int64_t)D * kH, o_w1 = o_b0 + kH, o_b1 = o_w1 + (int64_t)kH * kH, o_w2 = o_b1 + kH,
+                  o_b2 = o_w2 + (int64_t)kH * A;
+    rp.seg[sidx++] = RedSeg{ws.part_w0[n], 256 * 64, kDwCtaW0, D, kH, 64, 1, o_w0};          // W0[d][j] = part[j][d]
+    rp.seg[sidx++] = RedSeg{ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, o_b0};
+    rp.seg[sidx++] = RedSeg{ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, o_w1};
+    rp.seg[sidx++] = RedSeg{ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, o_b1};
+    rp.seg[sidx++] = RedSeg{ws.part_w2[n], 256 * 64, kDwCtaW2, kH, A, 64, 0, o_w2};
+    rp.seg[sidx++] = RedSeg{ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, o_b2};
+  }
+  rp.n_seg = sidx;
+  rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
+  rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
+  tc_reduce_kernel<<<2 * kNumSMs, 256, 0, st>>>(rp, grad_arena);
+  STX_LAUNCH_OK();
+  return STX_OK;
+}
+
+}  // namespace stx
