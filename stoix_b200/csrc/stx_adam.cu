@@ -79,9 +79,19 @@ __global__ void __launch_bounds__(kAdamThreads)
   // ---- phase 2 ----
   for (int s = 0; s < nseg; ++s) {
     const StxAdamSeg seg = segs[s];
-    double ss = 0.0;
-    const volatile double* vp = partials + (int64_t)s * gridDim.x;
-    for (unsigned int b = 0; b < gridDim.x; ++b) ss += vp[b];  // same order in every block
+    // every block re-reduces the per-block partials in the same fixed order (warp 0: lane-strided loads,
+    // xor-butterfly) and broadcasts through shared memory
+    __shared__ double s_ss;
+    if (threadIdx.x < 32) {
+      double part = 0.0;
+      const double* vp = partials + (int64_t)s * gridDim.x;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) part += __ldcg(vp + b);
+      part = warp_sum(part);
+      if (threadIdx.x == 0) s_ss = part;
+    }
+    __syncthreads();
+    const double ss = s_ss;
+    __syncthreads();
     const float g_norm = (float)sqrt(ss);
     // optax.clip_by_global_norm: trigger = g_norm < max_norm
     const float clip = (g_norm < seg.max_grad_norm) ? 1.0f : seg.max_grad_norm / g_norm;

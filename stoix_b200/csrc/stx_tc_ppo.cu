@@ -29,7 +29,8 @@ int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;
-constexpr int kFbThreads = 320;  // warp 0 gather producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kFbThreads = 416;  // warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5..12 epilogue
+constexpr int kFbMmaWarp = 4;
 
 // ---- K3a shared-memory map ------------------------------------------------------------------------
 constexpr uint32_t kOffW1 = 0;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], 1);
+      mbar_init(&x_full[s], 4);  // one arrival per producer warp
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(w_full, 1);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     tma_prefetch_desc(tmW0);
     tma_prefetch_desc(tmW1);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == kFbMmaWarp) tmem_alloc(tmem_slot, 512);
   {
     __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(smem + kOffW2);
     for (int i = threadIdx.x; i < kH * 16; i += kFbThreads) {
@@ -144,36 +145,38 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 
   float m_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actor_loss, entropy, value_loss, adv, pred value, target
 
-  if (warp == 0) {
-    // ===================== producer: weights by TMA, X rows by gather =====================
-    if (lane == 0) {
+  if (warp < 4) {
+    // ===================== producers: weights by TMA, X rows gathered one row per thread =====================
+    if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(w_full, 32768 + 131072);
       for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
       for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
     }
     const int dchunks = p.D >> 3;  // 16-byte chunks per observation row
+    const int r = threadIdx.x;     // row of the tile owned by this thread
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
-      if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) & 1) ^ 1, 1);
       const int tile = cta_in_net + it * ncta;
-      uint8_t* xs = smem + kOffX + s * 16384;
-#pragma unroll 4
-      for (int e = lane; e < kTileM * 8; e += 32) {
-        const int r = e >> 3, c = e & 7;
-        const int64_t mrow = (int64_t)tile * kTileM + r;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (c < dchunks) {
-          const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
-          v = *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8);
-        }
-        *reinterpret_cast<uint4*>(xs + r * 128 + ((c ^ (r & 7)) << 4)) = v;  // Swizzle<3,4,3>
-        if (which == 0) *reinterpret_cast<uint4*>(p.xg + mrow * 64 + c * 8) = v;
+      const int64_t mrow = (int64_t)tile * kTileM + r;
+      const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+      uint4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)  // 8 independent 16-byte loads in flight per thread
+        v[c] = c < dchunks ? *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+      if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) & 1) ^ 1, 1);
+      uint8_t* xs = smem + kOffX + s * 16384 + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
+      if (which == 0) {
+        uint4* xg = reinterpret_cast<uint4*>(p.xg + mrow * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xg[c] = v[c];
       }
       fence_async_proxy();
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_full[s]);
     }
-  } else if (warp == 1) {
+  } else if (warp == kFbMmaWarp) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_fwd = idesc_bf16(128, 256, 0, 1);   // B = W (in,out) image as MN-major
     constexpr uint32_t idesc_head = idesc_bf16(128, 16, 0, 1);
@@ -234,8 +237,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       __syncwarp();
     }
   } else {
-    // ===================== epilogue warps 2..9: lane quarter q, column half `half` =====================
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ===================== epilogue warps 5..12: lane quarter q = warp % 4, column half `half` =====================
+    const int q = warp & 3, half = (warp - 5) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
     const float inv_m = 1.0f / (float)p.mb;
@@ -245,6 +248,14 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
       const int g0 = 5 * it;
+      // per-row loss inputs: issued now, consumed in E2 (their latency hides behind E0/E1)
+      int pf_a = 0;
+      float pf_0 = 0.f, pf_1 = 0.f;
+      if (half == 0) {
+        const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+        if (net.is_actor) pf_a = p.action[src], pf_0 = p.logp_old[src], pf_1 = p.adv[src];
+        else pf_0 = p.v_old[src], pf_1 = p.tgt[src];
+      }
       // ---------------- E0 / E1: hidden layers ----------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
@@ -282,7 +293,6 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
-        const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
         float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dz[j] = 0.f;
@@ -299,8 +309,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           for (int j = 0; j < 16; ++j)
             if (j < A) se += expf(z[j] - zmax);
           const float lse = zmax + logf(se);
-          const int a = p.action[src];
-          const float adv = (p.adv[src] - adv_mean) * adv_rstd;
+          const int a = pf_a;
+          const float adv = (pf_1 - adv_mean) * adv_rstd;
           float ent = 0.f, logp_a = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -309,7 +319,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
               ent -= expf(lp) * lp;
               if (j == a) logp_a = lp;
             }
-          const float ratio = expf(logp_a - p.logp_old[src]);
+          const float ratio = expf(logp_a - pf_0);
           const float l1 = ratio * adv;
           const float l2 = fminf(fmaxf(ratio, 1.0f - p.clip_eps), 1.0f + p.clip_eps) * adv;
           const bool in_band = (ratio >= 1.0f - p.clip_eps) && (ratio <= 1.0f + p.clip_eps);
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             }
           m_acc[0] += -fminf(l1, l2), m_acc[1] += ent, m_acc[3] += adv;
         } else {
-          const float v = __uint_as_float(r[0]) + s_b2[0], vo = p.v_old[src], tg = p.tgt[src];
+          const float v = __uint_as_float(r[0]) + s_b2[0], vo = pf_0, tg = pf_1;
           const float diff = v - vo;
           const float vclip = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
           const float e1 = v - tg, e2 = vclip - tg, q1 = e1 * e1, q2 = e2 * e2;
@@ -414,7 +424,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       p.metric_part[(int64_t)blockIdx.x * 8 + threadIdx.x] = acc;
     }
   }
-  if (warp == 1) {
+  if (warp == kFbMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -567,17 +577,27 @@ struct RedParams {
   float inv_mb;
 };
 
-__global__ void tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
-  for (int s = 0; s < p.n_seg; ++s) {
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
+  // one flattened index space over all segments: every segment is reduced concurrently
+  int64_t total = 0;
+  for (int s = 0; s < p.n_seg; ++s) total += (int64_t)p.seg[s].rows * p.seg[s].cols;
+  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < total; gi += (int64_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    int64_t i = gi;
+    while (i >= (int64_t)p.seg[s].rows * p.seg[s].cols) i -= (int64_t)p.seg[s].rows * p.seg[s].cols, ++s;
     const RedSeg& g = p.seg[s];
-    const int64_t n = (int64_t)g.rows * g.cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const int r = (int)(i / g.cols), c = (int)(i % g.cols);
-      const int64_t so = g.transpose ? (int64_t)c * g.src_ld + r : (int64_t)r * g.src_ld + c;
-      float acc = 0.f;
-      for (int k = 0; k < g.n_part; ++k) acc += g.part[(int64_t)k * g.part_stride + so];
-      grad[g.dst_off + i] += p.weight * acc;
+    const int r = (int)(i / g.cols), c = (int)(i % g.cols);
+    const float* src = g.part + (g.transpose ? (int64_t)c * g.src_ld + r : (int64_t)r * g.src_ld + c);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // fixed association order -> deterministic
+    int k = 0;
+    for (; k + 4 <= g.n_part; k += 4) {
+      a0 += src[(int64_t)k * g.part_stride];
+      a1 += src[(int64_t)(k + 1) * g.part_stride];
+      a2 += src[(int64_t)(k + 2) * g.part_stride];
+      a3 += src[(int64_t)(k + 3) * g.part_stride];
     }
+    for (; k < g.n_part; ++k) a0 += src[(int64_t)k * g.part_stride];
+    grad[g.dst_off + i] += p.weight * ((a0 + a1) + (a2 + a3));
   }
   if (blockIdx.x == 0 && threadIdx.x < 6) {
     float acc = 0.f;
