@@ -84,11 +84,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   // W2 image: element (j, n) at (j/8)*256 + (n/8)*128 + (j%8)*16 + (n%8)*2, zero for n >= A
   {
-    __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(smem + kOffW2);
-    for (int i = threadIdx.x; i < kH * 16; i += kThreads) {
-      const int j = i >> 4, n = i & 15;
-      const __nv_bfloat16 v = n < p.A ? p.w2[j * p.A + n] : __float2bfloat16_rn(0.f);
-      w2s[((j >> 3) * 256 + (n >> 3) * 128 + (j & 7) * 16 + (n & 7) * 2) >> 1] = v;
+    // one thread per W2 row: all of its (<=16) loads are independent and in flight together
+    uint8_t* w2s = smem + kOffW2;
+    for (int j = threadIdx.x; j < kH; j += kThreads) {
+      uint32_t pk[8];
+      if (p.A == 8 && (reinterpret_cast<uintptr_t>(p.w2) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p.w2 + j * 8);
+        pk[0] = v.x, pk[1] = v.y, pk[2] = v.z, pk[3] = v.w, pk[4] = pk[5] = pk[6] = pk[7] = 0u;
+      } else {
+        unsigned short e[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) e[n] = n < p.A ? reinterpret_cast<const unsigned short*>(p.w2)[j * p.A + n] : (unsigned short)0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) pk[n] = (uint32_t)e[2 * n] | ((uint32_t)e[2 * n + 1] << 16);
+      }
+      uint8_t* dst = w2s + (j >> 3) * 256 + (j & 7) * 16;   // element (j, n) at (j/8)*256 + (n/8)*128 + (j%8)*16 + (n%8)*2
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) s_b0[i] = p.b0[i], s_b1[i] = p.b1[i];
     if (threadIdx.x < 16) s_b2[threadIdx.x] = threadIdx.x < p.A ? p.b2[threadIdx.x] : 0.f;
@@ -260,6 +272,24 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
 int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
                     uint32_t box_cols) {
   return make_map_2d(m, base, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// Tiled activation matrix [tiles*128 rows x 8*colgroups] (layout of stx_tc_ppo.cu::tiled_ptr) seen as a 2D
+// array of 8-byte words: inner = the 2 KB (128 rows x 16 B) block of one (tile, column group), outer =
+// tile*colgroups + group.  Box = 64 rows (128 words) x all column groups, no swizzle.
+int make_map_tiled(CUtensorMap* m, const void* base, uint64_t tiles, uint32_t colgroups) {
+  EncodeTiledFn enc = get_encode();
+  STX_REQUIRE(enc != nullptr, STX_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  STX_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, STX_E_ALIGN, "TMA source must be 16-byte aligned");
+  cuuint64_t dims[2] = {256, tiles * colgroups};
+  cuuint64_t strides[1] = {2048};
+  cuuint32_t box[2] = {128, colgroups};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  STX_REQUIRE(r == CUDA_SUCCESS, STX_E_ARG, "cuTensorMapEncodeTiled (tiled activations) failed with CUresult %d", (int)r);
+  return STX_OK;
 }
 
 static bool tc_shape_ok(const StxMlp* m) {

@@ -11,9 +11,12 @@
 //      from TMEM); W1's single smem image serves as MN-major B (forward) and K-major B (backward).
 //      Epilogue warps also emit h1, h2, dh2, dh1, dz (bf16) for the weight-gradient GEMMs, reduce the
 //      bias gradients with a shuffle butterfly and accumulate the loss metrics.
-//  tc_dw_kernel (K3b)  split-K GEMMs dW = A^T * B over the minibatch rows with both operands MN-major
-//      (TMA 64-column blocks, 3-stage mbarrier pipeline), 256 x N fp32 accumulators in TMEM:
-//        dW1 = h1^T dh2 (N=256), dW2 = h2^T dz (N=64 padded), dW0^T = dh1^T x (N=64 padded).
+//  tc_dw_kernel (K3b)  split-K GEMMs dW = A^T * B over the minibatch rows with both operands MN-major,
+//      3-stage TMA/mbarrier pipeline, 256 x N fp32 accumulators in TMEM:
+//        dW1 = h1^T dh2 (N=256), dW2 = h2^T dz (N=16), dW0^T = dh1^T x (N=64).
+//      The activations travel K3a -> K3b in a tiled layout [tile of 128 rows][8-column group][row][8]:
+//      a warp of K3a (one row per thread) stores 512 contiguous bytes per instruction, and one TMA box of
+//      K3b lands 64 rows of every column group as un-swizzled UMMA core matrices (8 rows x 16 B).
 //  tc_reduce_kernel     fixed-order reduction of the per-CTA partials into the flat fp32 gradient arena
 //      (deterministic; also the bias gradients and the six loss metrics).
 #include <cuda.h>
@@ -26,6 +29,7 @@ namespace tc {
 
 int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
                     uint32_t box_cols);  // stx_tc_mlp.cu (SWIZZLE_128B bf16)
+int make_map_tiled(CUtensorMap* m, const void* base, uint64_t tiles, uint32_t colgroups);  // stx_tc_mlp.cu
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;
@@ -46,8 +50,8 @@ constexpr uint32_t kFbSmemBytes = kOffBar + 128 + 1024;
 struct FbNet {
   const __nv_bfloat16* w2;   // [256 x A] bf16
   const float *b0, *b1, *b2;
-  __nv_bfloat16 *h1, *h2, *dh1, *dh2;  // [mb x 256]
-  __nv_bfloat16* dz;                   // [mb x 64] (columns >= A stay zero)
+  __nv_bfloat16 *h1, *h2, *dh1, *dh2;  // [mb x 256], tiled layout (see tiled_ptr)
+  __nv_bfloat16* dz;                   // [mb x 16] tiled (columns >= A are zero)
   float* db_part;                      // [n_cta_of_net][528]
   int A;
   int is_actor;
@@ -57,7 +61,7 @@ struct FbParams {
   FbNet net[2];
   int n_cta[2];             // CTAs per net (actor first)
   const __nv_bfloat16* obs; // [B x D]
-  __nv_bfloat16* xg;        // [mb x 64] gathered input rows (written by the actor CTAs)
+  __nv_bfloat16* xg;        // [mb x 64] gathered input rows, tiled layout (written by the actor CTAs)
   const int32_t* idx;       // perm + mb_off, or nullptr (then rows are row0 + i)
   int64_t row0;
   const int32_t* action;
@@ -67,6 +71,12 @@ struct FbParams {
   int mb;
   float clip_eps, ent_coef, vf_coef;
 };
+
+// Tiled activation layout shared by K3a (writer) and K3b (reader): element (row, col) of a [mb x 8*CG]
+// matrix lives at ((row/128 * CG + col/8) * 128 + row%128) * 8 + col%8.
+__device__ __forceinline__ uint4* tiled_ptr(__nv_bfloat16* base, int64_t row, int cg, int CG) {
+  return reinterpret_cast<uint4*>(base + (((row >> 7) * CG + cg) * 128 + (row & 127)) * 8);
+}
 
 // sum over the 32 lanes of a warp of v[i], i = 0..31: afterwards v[0] of lane l holds the total of
 // column l (reduce-scatter butterfly: 31 shuffles instead of 32 x 5).
@@ -127,11 +137,23 @@ __global__ void __launch_bounds__(kFbThreads, 1)
   }
   if (warp == kFbMmaWarp) tmem_alloc(tmem_slot, 512);
   {
-    __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(smem + kOffW2);
-    for (int i = threadIdx.x; i < kH * 16; i += kFbThreads) {
-      const int j = i >> 4, n = i & 15;
-      const __nv_bfloat16 v = n < net.A ? net.w2[j * net.A + n] : __float2bfloat16_rn(0.f);
-      w2s[((j >> 3) * 256 + (n >> 3) * 128 + (j & 7) * 16 + (n & 7) * 2) >> 1] = v;
+    // one thread per W2 row: all of its (<=16) loads are independent and in flight together
+    uint8_t* w2s = smem + kOffW2;
+    for (int j = threadIdx.x; j < kH; j += kFbThreads) {
+      uint32_t pk[8];
+      if (net.A == 8 && (reinterpret_cast<uintptr_t>(net.w2) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(net.w2 + j * 8);
+        pk[0] = v.x, pk[1] = v.y, pk[2] = v.z, pk[3] = v.w, pk[4] = pk[5] = pk[6] = pk[7] = 0u;
+      } else {
+        unsigned short e[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) e[n] = n < net.A ? reinterpret_cast<const unsigned short*>(net.w2)[j * net.A + n] : (unsigned short)0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) pk[n] = (uint32_t)e[2 * n] | ((uint32_t)e[2 * n + 1] << 16);
+      }
+      uint8_t* dst = w2s + (j >> 3) * 256 + (j & 7) * 16;   // element (j, n) at (j/8)*256 + (n/8)*128 + (j%8)*16 + (n%8)*2
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
     for (int i = threadIdx.x; i < 256; i += kFbThreads) s_b0[i] = net.b0[i], s_b1[i] = net.b1[i];
     if (threadIdx.x < 16) s_b2[threadIdx.x] = threadIdx.x < net.A ? net.b2[threadIdx.x] : 0.f;
@@ -168,9 +190,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 #pragma unroll
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
       if (which == 0) {
-        uint4* xg = reinterpret_cast<uint4*>(p.xg + mrow * 64);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xg[c] = v[c];
+        for (int c = 0; c < 8; ++c) *tiled_ptr(p.xg, mrow, c, 8) = v[c];
       }
       fence_async_proxy();
       __syncwarp();
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         tc_fence_after();
         const float* bias = layer == 0 ? s_b0 : s_b1;
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
-        __nv_bfloat16* hout = (layer == 0 ? net.h1 : net.h2) + mrow * kH;
+        __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c = half * 4 + cc;
@@ -277,9 +298,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             pk[j] = pack_bf16(v0, v1);
           }
           tmem_st16(ta + c * 16, pk);
-          uint4* dst = reinterpret_cast<uint4*>(hout + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
+            *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -358,9 +379,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         uint8_t* dzs = smem + kOffDz + (mr >> 3) * 256 + (mr & 7) * 16;
         *reinterpret_cast<uint4*>(dzs) = make_uint4(pk[0], pk[1], pk[2], pk[3]);        // k = 0..7
         *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
-        uint4* gz = reinterpret_cast<uint4*>(net.dz + mrow * 64);
-        gz[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        gz[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         fence_async_proxy();
       }
       tc_fence_before();
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         mbar_wait(mma_done, (g0 + 3 + (1 - layer)) & 1, 13 + layer);
         tc_fence_after();
         const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
-        __nv_bfloat16* dout = (layer == 1 ? net.dh2 : net.dh1) + mrow * kH;
+        __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -391,9 +411,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
           }
           if (layer == 1) tmem_st16(ta + c * 16, pk);  // dh2 replaces h2 as the A operand of G4
-          uint4* dst = reinterpret_cast<uint4*>(dout + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           const float cs = warp_colsum32(dv, lane);
           dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
         }
@@ -440,7 +460,7 @@ constexpr int kMaxJobs = 6;
 
 struct DwJob {
   float* part;     // [n_cta][256 x N] fp32 partial outputs
-  int N;           // 64 or 256
+  int N;           // 16, 64 or 256 (= 8 * column groups of B)
   int cta_begin;   // first CTA of this job
   int n_cta;
   int num_chunks;  // mb / 64
@@ -450,8 +470,8 @@ struct DwParams {
   int n_jobs;
 };
 struct DwMaps {
-  CUtensorMap a[kMaxJobs];  // [mb x 256] bf16, box 64 rows x 64 cols
-  CUtensorMap b[kMaxJobs];  // [mb x N]
+  CUtensorMap a[kMaxJobs];  // tiled [mb x 256]: 2D u64 view {256 per (tile, colgroup), tiles*32}, box {128, 32}
+  CUtensorMap b[kMaxJobs];  // tiled [mb x N]:   box {128, N/8}
 };
 
 __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
@@ -470,7 +490,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
   const DwJob& job = p.job[j];
   const int cta = (int)blockIdx.x - job.cta_begin;
   const int my_chunks = cta < job.num_chunks ? (job.num_chunks - cta + job.n_cta - 1) / job.n_cta : 0;
-  const int nblk = job.N >> 6;
+  const int cgb = job.N >> 3;  // column groups of B
   const uint32_t stage_tx = 32768 + (uint32_t)job.N * 128;
 
   if (threadIdx.x == 0) {
@@ -494,11 +514,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
       for (int it = 0; it < my_chunks; ++it) {
         const int s = it % kDwStages;
         if (it >= kDwStages) mbar_wait(&empty[s], ((it / kDwStages) & 1) ^ 1, 20);
-        const int row = (cta + it * job.n_cta) * 64;
+        const int chunk = cta + it * job.n_cta;          // 64 rows: half of a 128-row tile
+        const int tile = chunk >> 1, r0 = (chunk & 1) * 64;
         uint8_t* st = smem + s * kDwStageBytes;
         mbar_arrive_expect_tx(&full[s], stage_tx);
-        for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 8192, &maps.a[j], &full[s], b * 64, row);
-        for (int b = 0; b < nblk; ++b) tma_load_2d(st + 32768 + b * 8192, &maps.b[j], &full[s], b * 64, row);
+        // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
+        tma_load_2d(st, &maps.a[j], &full[s], r0 * 2, tile * 32);
+        tma_load_2d(st + 32768, &maps.b[j], &full[s], r0 * 2, tile * cgb);
       }
     }
   } else if (warp == 1) {
@@ -510,11 +532,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
       if (elect_one()) {
         const uint32_t a0 = sbase + s * kDwStageBytes, b0 = a0 + 32768;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {      // 16 rows (K) per step = two 8-row groups of 1024 B
+        for (int k = 0; k < 4; ++k) {      // 16 rows (K) per step = two core-matrix row groups of 128 B
 #pragma unroll
-          for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128)
-            mma_ss(tmem + h * 256, smem_desc(a0 + h * 16384 + k * 2048, 8192, 1024, SWIZZLE_128B),
-                   smem_desc(b0 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128) = column groups 16 h ..
+            mma_ss(tmem + h * 256, smem_desc(a0 + h * 16384 + k * 256, 128, 1024, SWIZZLE_NONE),
+                   smem_desc(b0 + k * 256, 128, 1024, SWIZZLE_NONE), idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty[s]);
       }
@@ -532,18 +554,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     }
     for (int h = 0; h < 2; ++h) {
       float* orow = out + (int64_t)(h * 128 + q * 32 + lane) * job.N;
-      for (int c = 0; c < job.N / 32; ++c) {
-        uint32_t r[32];
+      for (int c = 0; c < job.N / 16; ++c) {
+        uint32_t r[16];
         if (my_chunks > 0) {
-          tmem_ld32(tmem + lane_addr + h * 256 + c * 32, r);
+          tmem_ld16(tmem + lane_addr + h * 256 + c * 16, r);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
+          for (int i = 0; i < 16; ++i) r[i] = 0u;
         }
-        float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+        float4* dst = reinterpret_cast<float4*>(orow + c * 16);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
           dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                                __uint_as_float(r[4 * i + 3]));
       }
@@ -631,9 +653,9 @@ TcWs carve_tc(int64_t mb, char* base) {
     w.h2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.dh1[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.dh2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
-    w.dz[n] = (__nv_bfloat16*)take((size_t)mb * 64 * 2);
+    w.dz[n] = (__nv_bfloat16*)take((size_t)mb * 16 * 2);
     w.part_w1[n] = (float*)take((size_t)kDwCtaW1 * 65536 * 4);
-    w.part_w2[n] = (float*)take((size_t)kDwCtaW2 * 256 * 64 * 4);
+    w.part_w2[n] = (float*)take((size_t)kDwCtaW2 * 256 * 16 * 4);
     w.part_w0[n] = (float*)take((size_t)kDwCtaW0 * 256 * 64 * 4);
     w.db_part[n] = (float*)take((size_t)kCtaPerNet * 528 * 4);
   }
@@ -710,19 +732,20 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   int cta = 0, jn = 0;
   const int chunks = (int)(mb / 64);
   for (int n = 0; n < 2; ++n) {
+    const uint64_t tiles = (uint64_t)(mb / 128);
     // dW1 = h1^T dh2
-    if (int rc = make_map_2d_pub(&maps.a[jn], ws.h1[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
-    if (int rc = make_map_2d_pub(&maps.b[jn], ws.dh2[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
+    if (int rc = make_map_tiled(&maps.a[jn], ws.h1[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[jn], ws.dh2[n], tiles, 32)) return rc;
     dp.job[jn] = DwJob{ws.part_w1[n], 256, cta, kDwCtaW1, chunks};
     cta += kDwCtaW1, ++jn;
-    // dW2 = h2^T dz(padded to 64)
-    if (int rc = make_map_2d_pub(&maps.a[jn], ws.h2[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
-    if (int rc = make_map_2d_pub(&maps.b[jn], ws.dz[n], (uint64_t)mb, 64, 64, 64, 64)) return rc;
-    dp.job[jn] = DwJob{ws.part_w2[n], 64, cta, kDwCtaW2, chunks};
+    // dW2 = h2^T dz
+    if (int rc = make_map_tiled(&maps.a[jn], ws.h2[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[jn], ws.dz[n], tiles, 2)) return rc;
+    dp.job[jn] = DwJob{ws.part_w2[n], 16, cta, kDwCtaW2, chunks};
     cta += kDwCtaW2, ++jn;
-    // dW0^T = dh1^T x(padded to 64)
-    if (int rc = make_map_2d_pub(&maps.a[jn], ws.dh1[n], (uint64_t)mb, 256, 256, 64, 64)) return rc;
-    if (int rc = make_map_2d_pub(&maps.b[jn], ws.xg, (uint64_t)mb, 64, 64, 64, 64)) return rc;
+    // dW0^T = dh1^T x
+    if (int rc = make_map_tiled(&maps.a[jn], ws.dh1[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[jn], ws.xg, tiles, 8)) return rc;
     dp.job[jn] = DwJob{ws.part_w0[n], 64, cta, kDwCtaW0, chunks};
     cta += kDwCtaW0, ++jn;
   }
@@ -741,7 +764,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     rp.seg[sidx++] = RedSeg{ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, o_b0};
     rp.seg[sidx++] = RedSeg{ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, o_w1};
     rp.seg[sidx++] = RedSeg{ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, o_b1};
-    rp.seg[sidx++] = RedSeg{ws.part_w2[n], 256 * 64, kDwCtaW2, kH, A, 64, 0, o_w2};
+    rp.seg[sidx++] = RedSeg{ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, o_w2};
     rp.seg[sidx++] = RedSeg{ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, o_b2};
   }
   rp.n_seg = sidx;
