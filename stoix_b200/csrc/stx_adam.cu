@@ -35,7 +35,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
     __threadfence();
     const unsigned long long t = atomicAdd(arrive, 1ull);
     const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
-    while (*reinterpret_cast<volatile unsigned long long*>(arrive) < target) __nanosleep(32);
+    while (*reinterpret_cast<volatile unsigned long long*>(arrive) < target) {
+    }
     __threadfence();
   }
   __syncthreads();

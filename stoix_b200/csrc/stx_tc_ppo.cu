@@ -770,7 +770,11 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   rp.n_seg = sidx;
   rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
   rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
-  tc_reduce_kernel<<<2 * kNumSMs, 256, 0, st>>>(rp, grad_arena);
+  {
+    int64_t red_total = 0;
+    for (int i = 0; i < rp.n_seg; ++i) red_total += (int64_t)rp.seg[i].rows * rp.seg[i].cols;
+    tc_reduce_kernel<<<(unsigned)((red_total + 255) / 256), 256, 0, st>>>(rp, grad_arena);  // one element per thread
+  }
   STX_LAUNCH_OK();
   return STX_OK;
 }
