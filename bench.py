@@ -257,14 +257,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def progress(msg):
+        if os.environ.get("STX_BENCH_VERBOSE"):
+            print(f"[bench r{rank} {time.time() % 1000:.1f}] {msg}", file=sys.stderr, flush=True)
+
     # ---- warm-up (first update eager: module load / NCCL init; second captures the CUDA graph) ----
+    progress("setup done")
     l0 = lib.stx_launch_count()
     state = learn(state).learner_state
     torch.cuda.synchronize()
     launches_per_update = lib.stx_launch_count() - l0
+    progress("eager update done")
     for _ in range(max(args.warmup, 3)):
         state = learn(state).learner_state
     barrier()
+    progress("warm-up done")
 
     # ---- timed region A: device-resident (value) ----
     sampler = ClockSampler(local)
@@ -278,6 +285,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     dt = ev0.elapsed_time(ev1) * 1e-3
+    progress(f"timed region A done {dt:.3f}s")
 
     # ---- timed region B: end to end through the public API with host buffers (e2e) ----
     sh = learn.built["shards"][0]
@@ -304,6 +312,7 @@ def run_ours(args):
     barrier()
     dt_e2e = ev2.elapsed_time(ev3) * 1e-3
     clocks = sampler.stop()
+    progress("timed region B done")
 
     # ---- max over ranks ----
     times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
@@ -333,6 +342,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             phase_ms[name] = statistics.median(ts)
+            progress(f"phase {name} done")
         roll_f, upd_f = flops_per_env_step()
         upd_tflops = upd_f * T * E_PER_GPU / (phase_ms["update"] * 1e-3) / 1e12
         roofline = {"kernel": "K3 PPO minibatch forward/loss/backward (+K4 clip/Adam), 64 minibatch steps",
@@ -360,9 +370,13 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        # NCCL/TCPStore teardown can hang at interpreter exit in this container (observed: workers print their
+        # last line and never return to torchrun), so leave without running the destructors.
+        os._exit(0)
 
 
 def main():

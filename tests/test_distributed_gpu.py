@@ -48,7 +48,7 @@ if rank == 0:
     print(json.dumps({"params_identical_across_ranks": same, "changed": not torch.equal(p0, arena), "finite": bool(torch.isfinite(arena).all()),
                       "shards_differ": len({float(s) for s in sums}) == world,
                       "value_loss": float(out.train_metrics["value_loss"].mean())}))
-dist.barrier(); dist.destroy_process_group()
+dist.barrier(); torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)  # NCCL teardown can hang at exit here
 '''
 
 
