@@ -221,7 +221,8 @@ int launch_gae(const In& in, int T, int E, bool vec4, int standardize, float* ad
   } else if (vec4) {
     const int quads_total = E / 4;
     // Small E is latency-bound: more, smaller blocks.  Large E: 128-byte rows per warp access.
-    int quads = quads_total >= 8 * kNumSMs * 2 ? 8 : (quads_total >= 4 * kNumSMs ? 4 : 2);
+    // measured on B200 (profiles/r01_gae_bench.txt): wider rows per block win once the grid is large
+    int quads = quads_total >= 65536 ? 32 : (quads_total >= 8 * kNumSMs * 2 ? 8 : (quads_total >= 4 * kNumSMs ? 4 : 2));
     if (g_quads_override == 2 || g_quads_override == 4 || g_quads_override == 8 || g_quads_override == 16 ||
         g_quads_override == 32)
       quads = g_quads_override;
