@@ -514,7 +514,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
       for (int it = 0; it < my_chunks; ++it) {
         const int s = it % kDwStages;
         if (it >= kDwStages) mbar_wait(&empty[s], ((it / kDwStages) & 1) ^ 1, 20);
-        const int chunk = cta + it * job.n_cta;          // 64 rows: half of a 128-row tile
+        // newest rows first: K3a wrote the last tiles most recently, so they are the likeliest L2 residents
+        const int chunk = job.num_chunks - 1 - (cta + it * job.n_cta);  // 64 rows: half of a 128-row tile
         const int tile = chunk >> 1, r0 = (chunk & 1) * 64;
         uint8_t* st = smem + s * kDwStageBytes;
         mbar_arrive_expect_tx(&full[s], stage_tx);
