@@ -222,6 +222,19 @@ int stx_synth_env_step(int64_t E, int D, uint64_t seed, uint64_t step, const uin
                        int32_t* run_length, float* ep_return, int32_t* ep_length,
                        uint8_t* is_terminal, void* stream);
 
+/* Fused persistent rollout of the synthetic env on the bf16 tensor-core path: the T-step scan of _env_step
+ * (ff_ppo.py:81-140) for the actor side in ONE launch (grid = E/128 CTAs, each owning 128 envs for all T
+ * steps): logits -> Gumbel-max action + log_prob (same Philox counters as stx_categorical with seed
+ * cat_seed, call = cat_offset + t + *cat_counter) and the env step of stx_synth_env_step (step = env_step + t +
+ * *env_counter), trajectory written time-major: obs (T+1,E,D) bf16 [row 0 is the input], next_obs (T,E,D)
+ * bf16, the rest (T,E).  Bit-identical to the per-step path.  E % 128 == 0; actor as for STX_PREC_BF16. */
+int stx_tc_rollout_synth(const StxMlp* actor, void* obs, void* next_obs, int32_t* action, float* log_prob,
+                         float* reward, uint8_t* done, uint8_t* truncated, float* ep_return, int32_t* ep_length,
+                         uint8_t* is_terminal, float* run_return, int32_t* run_length, int T, int64_t E,
+                         uint64_t env_seed, uint64_t env_step, const uint64_t* env_counter, float p_term,
+                         float p_trunc, uint64_t cat_seed, uint64_t cat_offset, const uint64_t* cat_counter,
+                         void* stream);
+
 /* Utility casts used by the bf16 path (obs / weight shadows). */
 int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -81,6 +81,18 @@ class SyntheticBoxEnv(Environment):
                            out.reward, out.done, out.truncated, state["run_return"], state["run_length"],
                            out.episode_return, out.episode_length, out.is_terminal_step, dev_counter=state["counter"])
 
+    # -- whole-rollout face (bf16 tensor-core path) ---------------------------------------------------
+    fused_rollout_supported = True
+
+    def fused_rollout(self, state, actor_spec, actor_params, actor_params_bf16, shard, T: int, cat_seed: int, cat_counter) -> None:
+        """All T steps of policy + env in one persistent kernel (stx_tc_rollout_synth).  Valid because this
+        env's dynamics ignore the action, so the kernel generates step t+1's observation while the tensor cores
+        evaluate step t; the trajectory is bit-identical to T calls of step_into."""
+        ops.tc_rollout_synth(actor_spec, actor_params, actor_params_bf16, shard.obs, shard.next_obs, shard.action, shard.log_prob,
+                             shard.reward, shard.done, shard.truncated, shard.episode_return, shard.episode_length,
+                             shard.is_terminal_step, state["run_return"], state["run_length"], state["seed"], 0, state["counter"],
+                             self.p_term, self.p_trunc, cat_seed, 0, cat_counter)
+
     def advance(self, state, steps: int) -> None:
         """Move the device-resident step counter (end of a rollout; graph-capturable)."""
         ops.counter_add(state["counter"], steps)

@@ -391,6 +391,25 @@ def synth_env_step(E, D, seed, step, p_term, p_trunc, action, obs_out, next_obs,
     )
 
 
+def tc_rollout_synth(spec: MlpSpec, params, params_bf16, obs, next_obs, action, log_prob, reward, done, truncated, ep_return,
+                     ep_length, is_terminal, run_return, run_length, env_seed, env_step, env_counter, p_term, p_trunc, cat_seed,
+                     cat_offset, cat_counter) -> None:
+    """Fused T-step rollout of the synthetic env (stx_tc_rollout_synth); buffers are the time-major trajectory."""
+    _need_cuda(params, params_bf16, obs, next_obs, action, log_prob, reward, done, truncated, ep_return, ep_length, is_terminal,
+               run_return, run_length, env_counter, cat_counter)
+    if obs.dtype != torch.bfloat16 or next_obs.dtype != torch.bfloat16:
+        raise StxError("tc_rollout_synth: observation buffers must be bfloat16")
+    T, E = int(action.shape[0]), int(action.shape[1])
+    m = spec.c_struct(params, params_bf16)
+    _lib.check(
+        _lib.load().stx_tc_rollout_synth(C.byref(m), _p(obs), _p(next_obs), _p(action), _p(log_prob), _p(reward), _p(done), _p(truncated),
+                                         _p(ep_return), _p(ep_length), _p(is_terminal), _p(run_return), _p(run_length), T, E,
+                                         int(env_seed) & (2**64 - 1), int(env_step), _p(env_counter), float(p_term), float(p_trunc),
+                                         int(cat_seed) & (2**64 - 1), int(cat_offset), _p(cat_counter), _stream()),
+        "stx_tc_rollout_synth",
+    )
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(src)
     if out is None:

@@ -188,10 +188,16 @@ def get_learner_fn(
         sa, sc = b["sa"], b["sc"]
         c_tree = state.params.critic_params
         D = sa.sizes[0]
+        a_tree = state.params.actor_params
+        fused = (precision == ops.STX_PREC_BF16 and bool(arch.get("fused_rollout", True)) and E % 128 == 0
+                 and getattr(env, "fused_rollout_supported", False))
         for u in range(U):
             sh: _Shard = b["shards"][u]
-            for t in range(T):
-                _env_step(state, u, t, state.key)
+            if fused:  # whole T-step scan in one persistent launch (envs whose dynamics ignore the action)
+                env.fused_rollout(state.env_state[u], sa, a_tree.flat, a_tree.flat_bf16, sh, T, state.key[0] + u, b["roll_ctr"])
+            else:
+                for t in range(T):
+                    _env_step(state, u, t, state.key)
             # value = critic(obs_t), bootstrap_value = critic(next_obs_t) (ff_ppo.py:99,113-116), batched
             ops.mlp_forward(sc, c_tree.flat, sh.obs[:T].view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
                             out=sh.value.view(B, 1))

@@ -193,3 +193,42 @@ def test_learner_bf16_update_tracks_bf16_oracle():
     assert torch.equal(shadow, out.learner_state.params.actor_params.arena.to(torch.bfloat16))
     for name in ("actor_loss", "entropy", "value_loss"):
         np.testing.assert_allclose(f64(out.train_metrics[name][0]), metrics[name], rtol=2e-2, atol=2e-3)
+
+
+def test_fused_rollout_is_bit_identical_to_per_step_path():
+    """stx_tc_rollout_synth (one persistent launch for the T-step scan) must reproduce the per-step path
+    (forward kernel + stx_categorical + stx_synth_env_step per step) exactly: same Philox streams, same GEMMs."""
+    from stoix_b200 import random as srandom
+    from stoix_b200.config import compose
+    from stoix_b200.systems.ppo.anakin import ff_ppo
+    from stoix_b200.utils import make_env
+    from stoix_b200.utils.total_timestep_checker import check_total_timesteps
+
+    def run(fused):
+        E, T = 256, 12
+        cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E}", f"system.rollout_length={T}",
+                                         "system.num_minibatches=2", f"arch.total_timesteps={E * T * 2}", "arch.num_evaluation=1",
+                                         "arch.precision=bf16", f"arch.fused_rollout={fused}", "logger.use_console=False",
+                                         "env.kwargs.p_term=0.05", "env.kwargs.p_trunc=0.05"])
+        cfg.num_devices, cfg.rank = 1, 0
+        cfg = check_total_timesteps(cfg, quiet=True)
+        env, _ = make_env.make(cfg)
+        keys = srandom.split(srandom.PRNGKey(5), 4)
+        learn, _, state = ff_ppo.learner_setup(env, (keys[0], keys[2], keys[3]), cfg)
+        cfg.arch.num_updates_per_eval = 1
+        outs = []
+        for _ in range(2):
+            out = learn(state)
+            state = out.learner_state
+            torch.cuda.synchronize()
+            sh = learn.built["shards"][0]
+            outs.append({k: getattr(sh, k).clone() for k in ("obs", "next_obs", "action", "log_prob", "reward", "done", "truncated",
+                                                             "episode_return", "episode_length", "is_terminal_step", "value", "advantages")})
+        return outs, state.params.actor_params.arena.clone()
+
+    a, pa = run(True)
+    b, pb = run(False)
+    for upd in range(2):
+        for k in a[upd]:
+            assert torch.equal(a[upd][k], b[upd][k]), f"update {upd}: trajectory field {k} differs between fused and per-step rollout"
+    assert torch.equal(pa, pb)
