@@ -134,6 +134,10 @@ int stx_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t
 int stx_tc_debug_forward(const StxMlp* mlp, const void* x, int64_t ldx, int64_t M, float* out, float* h1,
                          float* h2, void* stream);
 
+/* Profiling hook: device buffer of >= 32 int64 that K3a's CTA 0 fills with clock64() stamps of its second
+ * tile (MMA-warp slots 0..9, first epilogue warp slots 16..27); NULL disables.  Synchronous (not for capture). */
+int stx_tc_debug_set_clock_buffer(long long* buf);
+
 /* Categorical head ops on logits (E, A) -- tfd.Categorical (stoix/networks/heads.py:41) as used at
  * ff_ppo.py:100-101.  If sample != 0: action = argmax_j(logits_j + Gumbel_j) with Philox4x32-10
  * keyed by seed with counter (row, call = offset + *dev_counter); else `action` is an input.

@@ -31,6 +31,13 @@ int make_map_2d_pub(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
                     uint32_t box_cols);  // stx_tc_mlp.cu (SWIZZLE_128B bf16)
 int make_map_tiled(CUtensorMap* m, const void* base, uint64_t tiles, uint32_t colgroups);  // stx_tc_mlp.cu
 
+// optional timeline instrumentation (scripts/profile_k3_timeline.py): clock64 stamps of CTA 0, tile 1
+__device__ long long* g_clock_buf = nullptr;
+#define STX_STAMP(slot)                                                              \
+  do {                                                                               \
+    if (g_clock_buf != nullptr && blockIdx.x == 0 && it == 1 && lane == 0) g_clock_buf[slot] = clock64(); \
+  } while (0)
+
 constexpr int kTileM = 128;
 constexpr int kH = 256;
 constexpr int kFbThreads = 416;  // warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5..12 epilogue
@@ -207,9 +214,11 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       const int g0 = 5 * it;
+      STX_STAMP(0);
       mbar_wait(&x_full[s], (it >> 1) & 1, 3);
       if (g0 > 0) mbar_wait(epi_done, (g0 - 1) & 1, 4);
       tc_fence_after();
+      STX_STAMP(1);
       if (elect_one()) {  // G0: D = X * W0
         const uint32_t xa = sbase + kOffX + s * 16384;
 #pragma unroll
@@ -220,8 +229,10 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         mma_commit(mma_done);
       }
       __syncwarp();
+      STX_STAMP(2);
       mbar_wait(epi_done, g0 & 1, 5);
       tc_fence_after();
+      STX_STAMP(3);
       if (elect_one()) {  // G1: D = h1 * W1
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -229,8 +240,10 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         mma_commit(mma_done);
       }
       __syncwarp();
+      STX_STAMP(4);
       mbar_wait(epi_done, (g0 + 1) & 1, 6);
       tc_fence_after();
+      STX_STAMP(5);
       if (elect_one()) {  // G2: D[:, :16] = h2 * W2
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -238,16 +251,20 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         mma_commit(mma_done);
       }
       __syncwarp();
+      STX_STAMP(6);
       mbar_wait(epi_done, (g0 + 2) & 1, 7);
       tc_fence_after();
+      STX_STAMP(7);
       if (elect_one()) {  // G3: D = dz (smem, K-major core matrices) * W2^T (same W2 image, K-major)
         mma_ss(tmem_d, smem_desc(sbase + kOffDz, 128, 256, SWIZZLE_NONE), smem_desc(sbase + kOffW2, 128, 256, SWIZZLE_NONE),
                idesc_bwd, 0);
         mma_commit(mma_done);
       }
       __syncwarp();
+      STX_STAMP(8);
       mbar_wait(epi_done, (g0 + 3) & 1, 8);
       tc_fence_after();
+      STX_STAMP(9);
       if (elect_one()) {  // G4: D = dh2 * W1^T  (W1 image as K-major SW128: 4 K-blocks of 64)
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -280,8 +297,10 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       // ---------------- E0 / E1: hidden layers ----------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
+        if (warp == 5) STX_STAMP(16 + 2 * layer);
         mbar_wait(mma_done, (g0 + layer) & 1, 10 + layer);
         tc_fence_after();
+        if (warp == 5) STX_STAMP(17 + 2 * layer);
         const float* bias = layer == 0 ? s_b0 : s_b1;
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
         __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
@@ -308,8 +327,10 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         if (lane == 0) mbar_arrive(epi_done);
       }
       // ---------------- E2: head + loss + d(head) ----------------
+      if (warp == 5) STX_STAMP(20);
       mbar_wait(mma_done, (g0 + 2) & 1, 12);
       tc_fence_after();
+      if (warp == 5) STX_STAMP(21);
       if (half == 0) {
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
@@ -389,8 +410,10 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       // ---------------- E3 / E4: dh2 = D * (h2 > 0) ; dh1 = D * (h1 > 0) ----------------
 #pragma unroll 1
       for (int layer = 1; layer >= 0; --layer) {
+        if (warp == 5) STX_STAMP(22 + 2 * (1 - layer));
         mbar_wait(mma_done, (g0 + 3 + (1 - layer)) & 1, 13 + layer);
         tc_fence_after();
+        if (warp == 5) STX_STAMP(23 + 2 * (1 - layer));
         const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
         __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
@@ -421,6 +444,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
+        if (warp == 5) STX_STAMP(26 + (1 - layer));
       }
     }
   }
@@ -781,3 +805,8 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
 }
 
 }  // namespace stx
+
+extern "C" int stx_tc_debug_set_clock_buffer(long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(stx::tc::g_clock_buf, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : (int)e;
+}
