@@ -282,6 +282,13 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     const float inv_m = 1.0f / (float)p.mb;
     float adv_mean = 0.f, adv_rstd = 1.f;
     if (p.adv_stats) adv_mean = p.adv_stats[0], adv_rstd = p.adv_stats[1];
+    // source row of this thread's row in the NEXT tile: loaded one tile ahead so that the dependent per-row
+    // loads below never wait on the index (two chained DRAM latencies would otherwise open every tile)
+    int64_t src_next = 0;
+    if (half == 0 && my_tiles > 0) {
+      const int64_t r0 = (int64_t)cta_in_net * kTileM + q * 32 + lane;
+      src_next = p.idx ? (int64_t)p.idx[r0] : p.row0 + r0;
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
@@ -290,9 +297,13 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       int pf_a = 0;
       float pf_0 = 0.f, pf_1 = 0.f;
       if (half == 0) {
-        const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+        const int64_t src = src_next;
         if (net.is_actor) pf_a = p.action[src], pf_0 = p.logp_old[src], pf_1 = p.adv[src];
         else pf_0 = p.v_old[src], pf_1 = p.tgt[src];
+        if (it + 1 < my_tiles) {
+          const int64_t rn = mrow + (int64_t)ncta * kTileM;
+          src_next = p.idx ? (int64_t)p.idx[rn] : p.row0 + rn;
+        }
       }
       // ---------------- E0 / E1: hidden layers ----------------
 #pragma unroll 1
@@ -386,11 +397,21 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         }
         // bias gradient of the head: column sums over the 32 rows of this warp (16 columns)
         {
-          float t[32];
+          // 16 columns: fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
+          float t[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) t[j] = dz[j], t[16 + j] = 0.f;
-          const float cs = warp_colsum32(t, lane);
-          if (lane < 16) s_db[q * 528 + 512 + lane] += cs;
+          for (int j = 0; j < 16; ++j) t[j] = dz[j] + __shfl_xor_sync(0xffffffffu, dz[j], 16);
+#pragma unroll
+          for (int s2 = 8; s2 >= 1; s2 >>= 1) {
+#pragma unroll
+            for (int i = 0; i < s2; ++i) {
+              const bool hi = (lane & s2) != 0;
+              const float send = hi ? t[i] : t[i + s2];
+              const float keep = hi ? t[i + s2] : t[i];
+              t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+            }
+          }
+          if (lane < 16) s_db[q * 528 + 512 + lane] += t[0];  // lanes 0..15 hold columns 0..15
         }
         // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
         uint32_t pk[8];
