@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 #pragma unroll
       for (int c = 0; c < 8; ++c)  // 8 independent 16-byte loads in flight per thread
         v[c] = c < dchunks ? *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+      if (warp == 0) STX_STAMP(48);
       if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) & 1) ^ 1, 1);
+      if (warp == 0) STX_STAMP(49);
       uint8_t* xs = smem + kOffX + s * 16384 + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
@@ -200,7 +202,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 #pragma unroll
         for (int c = 0; c < 8; ++c) *tiled_ptr(p.xg, mrow, c, 8) = v[c];
       }
+      if (warp == 0) STX_STAMP(50);
       fence_async_proxy();
+      if (warp == 0) STX_STAMP(51);
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_full[s]);
     }
@@ -346,33 +350,39 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
+        if (warp == 5) STX_STAMP(40);
         float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dz[j] = 0.f;
         if (net.is_actor) {
           const int A = net.A;
-          float z[16], zmax = -INFINITY;
+          // softmax statistics with ONE exponential per logit: e_j = exp(z_j - zmax), p_j = e_j / sum(e),
+          // log p_j = (z_j - zmax) - log(sum(e)).  Fast intrinsics: this path carries bf16-level error anyway.
+          float zs[16], ex[16], zmax = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            z[j] = __uint_as_float(r[j]) + s_b2[j];
-            if (j < A) zmax = fmaxf(zmax, z[j]);
+            zs[j] = __uint_as_float(r[j]) + s_b2[j];
+            if (j < A) zmax = fmaxf(zmax, zs[j]);
           }
           float se = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < A) se += expf(z[j] - zmax);
-          const float lse = zmax + logf(se);
+          for (int j = 0; j < 16; ++j) {
+            zs[j] -= zmax;
+            ex[j] = j < A ? __expf(zs[j]) : 0.f;
+            se += ex[j];
+          }
+          const float lse = __logf(se), inv_se = 1.0f / se;
           const int a = pf_a;
           const float adv = (pf_1 - adv_mean) * adv_rstd;
           float ent = 0.f, logp_a = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < A) {
-              const float lp = z[j] - lse;
-              ent -= expf(lp) * lp;
+              const float lp = zs[j] - lse;
+              ent -= ex[j] * inv_se * lp;
               if (j == a) logp_a = lp;
             }
-          const float ratio = expf(logp_a - pf_0);
+          const float ratio = __expf(logp_a - pf_0);
           const float l1 = ratio * adv;
           const float l2 = fminf(fmaxf(ratio, 1.0f - p.clip_eps), 1.0f + p.clip_eps) * adv;
           const bool in_band = (ratio >= 1.0f - p.clip_eps) && (ratio <= 1.0f + p.clip_eps);
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < A) {
-              const float lp = z[j] - lse, pr = expf(lp);
+              const float lp = zs[j] - lse, pr = ex[j] * inv_se;
               dz[j] = dlogp * ((j == a ? 1.f : 0.f) - pr) + ce * pr * (lp + ent);
             }
           m_acc[0] += -fminf(l1, l2), m_acc[1] += ent, m_acc[3] += adv;
@@ -395,6 +405,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           dz[0] = p.vf_coef * dv * inv_m;
           m_acc[2] += 0.5f * fmaxf(q1, q2), m_acc[4] += v, m_acc[5] += tg;
         }
+        if (warp == 5) STX_STAMP(41);
         // bias gradient of the head: column sums over the 32 rows of this warp (16 columns)
         {
           // 16 columns: fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           }
           if (lane < 16) s_db[q * 528 + 512 + lane] += t[0];  // lanes 0..15 hold columns 0..15
         }
+        if (warp == 5) STX_STAMP(42);
         // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
         uint32_t pk[8];
 #pragma unroll
@@ -423,7 +435,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
         *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (warp == 5) STX_STAMP(43);
         fence_async_proxy();
+        if (warp == 5) STX_STAMP(44);
       }
       tc_fence_before();
       __syncwarp();
