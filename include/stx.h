@@ -62,6 +62,10 @@ typedef struct StxPpoHyper {
   float ent_coef;
   float vf_coef;
   int32_t standardize_advantages; /* 1: use (adv - stats[0]) * stats[1] on load (multistep.py:138-139) */
+  int32_t overwrite_grads;        /* 1: grad_arena = weight * g (no prior zero fill needed); 0: grad_arena += weight * g */
+  int32_t reserved;
+  void* adam_scratch;             /* nullable; bf16 path with overwrite_grads: also leave sum(g^2) partials of both
+                                     optimiser segments in this stx_clip_adam_step scratch (then call it with prenorm = 1) */
 } StxPpoHyper;
 
 /* One optimiser = optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps=1e-5))
@@ -79,6 +83,8 @@ typedef struct StxAdamHyper {
   int32_t decay;             /* system.decay_learning_rates: lr(k) = init_lr*(1-(k // steps_per_update)/num_updates), utils/training.py:24-26 */
   int32_t steps_per_update;  /* epochs * num_minibatches */
   int32_t num_updates;       /* arch.num_updates */
+  int32_t prenorm;           /* 1: the scratch already holds the sum-of-squares partials of the (unscaled) gradients,
+                                written by stx_ppo_minibatch_grads(adam_scratch): skip the norm pass and the grid barrier */
 } StxAdamHyper;
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -32,6 +32,9 @@ class StxPpoHyper(C.Structure):
         ("ent_coef", C.c_float),
         ("vf_coef", C.c_float),
         ("standardize_advantages", C.c_int32),
+        ("overwrite_grads", C.c_int32),
+        ("reserved", C.c_int32),
+        ("adam_scratch", C.c_void_p),
     ]
 
 
@@ -53,6 +56,7 @@ class StxAdamHyper(C.Structure):
         ("decay", C.c_int32),
         ("steps_per_update", C.c_int32),
         ("num_updates", C.c_int32),
+        ("prenorm", C.c_int32),
     ]
 
 

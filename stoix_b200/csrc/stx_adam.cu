@@ -42,6 +42,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
   __syncthreads();
 }
 
+template <bool PRENORM>
 __global__ void __launch_bounds__(kAdamThreads)
     clip_adam_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ MU,
                      float* __restrict__ NU, int32_t* __restrict__ counts,
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(kAdamThreads)
   const int gthreads = gridDim.x * blockDim.x;
 
   // ---- phase 1: per-segment sum of squares of (grad * grad_scale) ----
-  for (int s = 0; s < nseg; ++s) {
+  // (PRENORM: the producer of the gradients already left sum(g^2) partials of the unscaled gradients here)
+  for (int s = 0; s < nseg && !PRENORM; ++s) {
     const StxAdamSeg seg = segs[s];
     const float4* g4 = reinterpret_cast<const float4*>(G + seg.offset);
     const int64_t n4 = seg.count / 4;
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kAdamThreads)
   int32_t cnt[kAdamMaxSegs], sch[kAdamMaxSegs];
   for (int s = 0; s < nseg; ++s) cnt[s] = counts[2 * s], sch[s] = counts[2 * s + 1];
 
-  grid_barrier(&scratch->arrive);
+  if (!PRENORM) grid_barrier(&scratch->arrive);
 
   // ---- phase 2 ----
   for (int s = 0; s < nseg; ++s) {
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kAdamThreads)
       if (threadIdx.x == 0) s_ss = part;
     }
     __syncthreads();
-    const double ss = s_ss;
+    const double ss = PRENORM ? s_ss * (double)h.grad_scale * (double)h.grad_scale : s_ss;
     __syncthreads();
     const float g_norm = (float)sqrt(ss);
     // optax.clip_by_global_norm: trigger = g_norm < max_norm
@@ -189,9 +191,14 @@ extern "C" int stx_clip_adam_step(float* param_arena, const float* grad_arena, f
               "stx_clip_adam_step: steps_per_update/num_updates must be positive");
   // The grid is fixed (one wave) so the barrier ticket arithmetic is launch-invariant.
   const int grid = kNumSMs;
-  clip_adam_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
-      param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
-      reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
+  if (hyper->prenorm)
+    clip_adam_kernel<true><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+        param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
+        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
+  else
+    clip_adam_kernel<false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+        param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
+        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
   STX_LAUNCH_OK();
   (void)adam_grid;
   return STX_OK;

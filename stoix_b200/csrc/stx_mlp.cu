@@ -161,7 +161,7 @@ SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
 
 // backward of one network given d(head) in ws.dhead; accumulates grad_weight * grads into net_grad.
 int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t mb,
-                  const SimtPpoWs& ws, float grad_weight, float* net_grad, cudaStream_t st) {
+                  const SimtPpoWs& ws, float grad_weight, float* net_grad, int overwrite, cudaStream_t st) {
   int64_t woff[STX_MAX_LAYERS], boff[STX_MAX_LAYERS];
   layer_offsets(m, woff, boff);
   const int64_t np = stx_mlp_param_count(m);
@@ -199,7 +199,7 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
       pp ^= 1;
     }
   }
-  simt::reduce_partials_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ws.partials, ws.splits, np, np, grad_weight, net_grad);
+  simt::reduce_partials_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ws.partials, ws.splits, np, np, grad_weight, net_grad, overwrite);
   STX_LAUNCH_OK();
   return STX_OK;
 }
@@ -317,7 +317,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
     g.partials = ws.loss_partials, g.counter = ws.counter, g.metrics = metrics, g.weight = grad_weight;
     ppo_loss_grad_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, st>>>(g);
     STX_LAUNCH_OK();
-    if (int rc = simt_backward(actor, x, D, idx, mb, ws, grad_weight, grad_arena + aoff, st)) return rc;
+    if (int rc = simt_backward(actor, x, D, idx, mb, ws, grad_weight, grad_arena + aoff, h->overwrite_grads, st)) return rc;
   }
   // ---- critic: forward, loss, backward (ff_ppo.py:215-235, 244-247) ----
   {
@@ -331,7 +331,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
     g.partials = ws.loss_partials, g.counter = ws.counter, g.metrics = metrics, g.weight = grad_weight;
     ppo_loss_grad_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, st>>>(g);
     STX_LAUNCH_OK();
-    if (int rc = simt_backward(critic, x, D, idx, mb, ws, grad_weight, grad_arena + coff, st)) return rc;
+    if (int rc = simt_backward(critic, x, D, idx, mb, ws, grad_weight, grad_arena + coff, h->overwrite_grads, st)) return rc;
   }
   return STX_OK;
 }

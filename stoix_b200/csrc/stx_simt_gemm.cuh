@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
 
 // grad[i] += w * sum_z part[z*stride + i]   (fixed order over z -> deterministic)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride,
-                                       int64_t n, float w, float* __restrict__ grad) {
+                                       int64_t n, float w, float* __restrict__ grad, int overwrite) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
-  grad[i] += w * s;
+  grad[i] = overwrite ? w * s : grad[i] + w * s;
 }
 
 }  // namespace simt

@@ -641,45 +641,88 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
 
 // =============================== reduce partials -> gradient arena ================================
 struct RedSeg {
-  const float* part;   // partial base
-  int64_t part_stride; // floats between CTAs' partials
+  const float* part;    // partial base (source view: rows x cols with leading dimension src_ld)
+  int64_t part_stride;  // floats between the partials of consecutive CTAs
   int n_part;
-  int rows, cols;      // destination matrix (rows x cols) at grad + dst_off, row-major
-  int src_ld;          // leading dimension of one partial
-  int transpose;       // 1: dst[r][c] = src[c][r]
+  int rows, cols;       // elements to take from the source view
+  int src_ld;
+  int transpose;        // 0: dst[r*dst_ld + c]   1: dst[c*dst_ld + r]
+  int dst_ld;
   int64_t dst_off;
+  int net;              // optimiser segment (0 actor, 1 critic) for the sum-of-squares side output
+  int vec;              // 1: process 4 consecutive columns per item with 128-bit accesses
+  int items;            // rows*cols/4 (vec) or rows*cols
 };
 struct RedParams {
   RedSeg seg[12];
   int n_seg;
+  int total_items;
   const float* metric_part;  // [n_cta_total][8]
   int n_cta_total;
   float* metrics;            // [6] accumulated
   float weight;
   float inv_mb;
+  int overwrite;
+  double* sumsq;             // nullable: [2][gridDim] block partials of sum((weight*g)^2) per optimiser segment
 };
 
-__global__ void __launch_bounds__(256) tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
-  // one flattened index space over all segments: every segment is reduced concurrently
-  int64_t total = 0;
-  for (int s = 0; s < p.n_seg; ++s) total += (int64_t)p.seg[s].rows * p.seg[s].cols;
-  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < total; gi += (int64_t)gridDim.x * blockDim.x) {
-    int s = 0;
-    int64_t i = gi;
-    while (i >= (int64_t)p.seg[s].rows * p.seg[s].cols) i -= (int64_t)p.seg[s].rows * p.seg[s].cols, ++s;
+constexpr int kRedThreads = 1024;
+
+// Fixed-order reduction of the per-CTA partials into the gradient arena.  One launch, every segment
+// concurrently; 4 independent accumulators per element for load-level parallelism; the association order
+// is fixed => run-to-run deterministic gradients.  Optionally leaves the per-block sum of squares of the
+// reduced gradient for the fused optimiser (which can then skip its own norm pass and grid barrier).
+__global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
+  double sq[2] = {0.0, 0.0};
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < p.total_items; gi += gridDim.x * blockDim.x) {
+    int s = 0, i = gi;
+    while (i >= p.seg[s].items) i -= p.seg[s].items, ++s;
     const RedSeg& g = p.seg[s];
-    const int r = (int)(i / g.cols), c = (int)(i % g.cols);
-    const float* src = g.part + (g.transpose ? (int64_t)c * g.src_ld + r : (int64_t)r * g.src_ld + c);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // fixed association order -> deterministic
-    int k = 0;
-    for (; k + 4 <= g.n_part; k += 4) {
-      a0 += src[(int64_t)k * g.part_stride];
-      a1 += src[(int64_t)(k + 1) * g.part_stride];
-      a2 += src[(int64_t)(k + 2) * g.part_stride];
-      a3 += src[(int64_t)(k + 3) * g.part_stride];
+    if (g.vec) {
+      const int cpr = g.cols >> 2;  // float4 items per row
+      const int r = i / cpr, c = (i % cpr) << 2;
+      const float* src = g.part + (int64_t)r * g.src_ld + c;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      int k = 0;
+      for (; k + 2 <= g.n_part; k += 2) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (int64_t)k * g.part_stride);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + (int64_t)(k + 1) * g.part_stride);
+        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+        a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
+      }
+      if (k < g.n_part) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (int64_t)k * g.part_stride);
+        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+      }
+      float4 o = make_float4(p.weight * (a0.x + a1.x), p.weight * (a0.y + a1.y), p.weight * (a0.z + a1.z), p.weight * (a0.w + a1.w));
+      float4* dst = reinterpret_cast<float4*>(grad + g.dst_off + (int64_t)r * g.dst_ld + c);
+      if (!p.overwrite) {
+        const float4 old = *dst;
+        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+      }
+      *dst = o;
+      sq[g.net] += (double)o.x * o.x + (double)o.y * o.y + (double)o.z * o.z + (double)o.w * o.w;
+    } else {
+      const int r = i / g.cols, c = i % g.cols;
+      const float* src = g.part + (int64_t)r * g.src_ld + c;
+      float a0 = 0.f, a1 = 0.f;
+      int k = 0;
+      for (; k + 2 <= g.n_part; k += 2) a0 += src[(int64_t)k * g.part_stride], a1 += src[(int64_t)(k + 1) * g.part_stride];
+      if (k < g.n_part) a0 += src[(int64_t)k * g.part_stride];
+      float* dst = grad + g.dst_off + (g.transpose ? (int64_t)c * g.dst_ld + r : (int64_t)r * g.dst_ld + c);
+      float o = p.weight * (a0 + a1);
+      if (!p.overwrite) o += *dst;
+      *dst = o;
+      sq[g.net] += (double)o * o;
     }
-    for (; k < g.n_part; ++k) a0 += src[(int64_t)k * g.part_stride];
-    grad[g.dst_off + i] += p.weight * ((a0 + a1) + (a2 + a3));
+  }
+  if (p.sumsq != nullptr) {  // only meaningful with overwrite (then o is the whole gradient)
+    __shared__ double sred[32];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const double b = block_sum<double>(sq[n], sred);
+      if (threadIdx.x == 0) p.sumsq[(int64_t)n * gridDim.x + blockIdx.x] = b;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < 6) {
     float acc = 0.f;
@@ -816,25 +859,34 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   // ---- reduce ----
   RedParams rp{};
   int sidx = 0;
+  auto add_seg = [&](const float* part, int64_t stride, int n_part, int rows, int cols, int src_ld, int transpose, int dst_ld,
+                     int64_t dst_off, int net_id) {
+    RedSeg g{};
+    g.part = part, g.part_stride = stride, g.n_part = n_part, g.rows = rows, g.cols = cols, g.src_ld = src_ld;
+    g.transpose = transpose, g.dst_ld = dst_ld, g.dst_off = dst_off, g.net = net_id;
+    g.vec = (!transpose && cols % 4 == 0 && dst_ld % 4 == 0 && dst_off % 4 == 0 && src_ld % 4 == 0 && stride % 4 == 0) ? 1 : 0;
+    g.items = g.vec ? rows * cols / 4 : rows * cols;
+    rp.total_items += g.items;
+    rp.seg[sidx++] = g;
+  };
   for (int n = 0; n < 2; ++n) {
     const int A = nets[n]->sizes[3];
     const int64_t o_w0 = noff[n], o_b0 = o_w0 + (int64_t)D * kH, o_w1 = o_b0 + kH, o_b1 = o_w1 + (int64_t)kH * kH, o_w2 = o_b1 + kH,
                   o_b2 = o_w2 + (int64_t)kH * A;
-    rp.seg[sidx++] = RedSeg{ws.part_w0[n], 256 * 64, kDwCtaW0, D, kH, 64, 1, o_w0};          // W0[d][j] = part[j][d]
-    rp.seg[sidx++] = RedSeg{ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, o_b0};
-    rp.seg[sidx++] = RedSeg{ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, o_w1};
-    rp.seg[sidx++] = RedSeg{ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, o_b1};
-    rp.seg[sidx++] = RedSeg{ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, o_w2};
-    rp.seg[sidx++] = RedSeg{ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, o_b2};
+    add_seg(ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, kH, o_w1, n);              // dW1[in][out]
+    add_seg(ws.part_w0[n], 256 * 64, kDwCtaW0, kH, D, 64, 1, kH, o_w0, n);             // part[j][d] -> W0[d][j]
+    add_seg(ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, A, o_w2, n);              // dW2[j][a]
+    add_seg(ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b0, n);
+    add_seg(ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b1, n);
+    add_seg(ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, A, o_b2, n);
   }
   rp.n_seg = sidx;
   rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
   rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
-  {
-    int64_t red_total = 0;
-    for (int i = 0; i < rp.n_seg; ++i) red_total += (int64_t)rp.seg[i].rows * rp.seg[i].cols;
-    tc_reduce_kernel<<<(unsigned)((red_total + 255) / 256), 256, 0, st>>>(rp, grad_arena);  // one element per thread
-  }
+  rp.overwrite = h->overwrite_grads;
+  // side output for the fused optimiser: partials[seg][block] right after the 16-byte header of its scratch
+  rp.sumsq = (h->overwrite_grads && h->adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->adam_scratch) + 16) : nullptr;
+  tc_reduce_kernel<<<kNumSMs, kRedThreads, 0, st>>>(rp, grad_arena);
   STX_LAUNCH_OK();
   return STX_OK;
 }

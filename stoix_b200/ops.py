@@ -269,7 +269,8 @@ def ppo_minibatch_grads(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tens
                         mb_off: int, mb: int, clip_eps: float, ent_coef: float, vf_coef: float,
                         standardize: bool, grad_arena: torch.Tensor, metrics: torch.Tensor,
                         workspace: torch.Tensor, precision: int = STX_PREC_F32, grad_weight: float = 1.0,
-                        param_arena_bf16: Optional[torch.Tensor] = None) -> None:
+                        param_arena_bf16: Optional[torch.Tensor] = None, overwrite: bool = False,
+                        adam_scratch: Optional[torch.Tensor] = None) -> None:
     """Accumulate grad_weight * d(loss)/d(params) of minibatch [mb_off, mb_off+mb) into grad_arena and
     the six loss metrics into `metrics` (ff_ppo.py:184-247)."""
     _need_cuda(param_arena, batch.obs, batch.action, batch.log_prob, batch.value, batch.advantages,
@@ -286,7 +287,8 @@ def ppo_minibatch_grads(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tens
     a = actor.c_struct(param_arena, param_arena_bf16)
     c = critic.c_struct(param_arena[coff:], param_arena_bf16[coff:] if param_arena_bf16 is not None else None)
     b = batch.c_struct()
-    h = _lib.StxPpoHyper(float(clip_eps), float(ent_coef), float(vf_coef), int(bool(standardize)))
+    h = _lib.StxPpoHyper(float(clip_eps), float(ent_coef), float(vf_coef), int(bool(standardize)), int(bool(overwrite)), 0,
+                         adam_scratch.data_ptr() if adam_scratch is not None else None)
     _lib.check(
         lib.stx_ppo_minibatch_grads(C.byref(a), C.byref(c), C.byref(b), int(mb_off), int(mb), C.byref(h),
                                     float(grad_weight), _p(grad_arena), _p(metrics), precision,
@@ -336,13 +338,14 @@ class AdamPlan:
         self.gnorm = torch.zeros(self.nseg, dtype=torch.float32, device=device)
         self.scratch = torch.zeros(int(_lib.load().stx_adam_scratch_bytes(self.nseg)), dtype=torch.uint8, device=device)
         self.hyper = _lib.StxAdamHyper(float(b1), float(b2), float(eps), 1.0, int(bool(decay)),
-                                       int(steps_per_update), int(num_updates))
+                                       int(steps_per_update), int(num_updates), 0)
 
 
 def clip_adam_step(plan: AdamPlan, params: torch.Tensor, grads: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor,
-                   grad_scale: float = 1.0, params_bf16: Optional[torch.Tensor] = None) -> None:
+                   grad_scale: float = 1.0, params_bf16: Optional[torch.Tensor] = None, prenorm: bool = False) -> None:
     _need_cuda(params, grads, mu, nu, params_bf16)
     plan.hyper.grad_scale = float(grad_scale)
+    plan.hyper.prenorm = int(bool(prenorm))
     lib = _lib.load()
     _lib.check(
         lib.stx_clip_adam_step(_p(params), _p(grads), _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg,

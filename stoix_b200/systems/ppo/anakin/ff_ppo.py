@@ -232,17 +232,20 @@ def get_learner_fn(
                 ops.make_permutation(B, seeds[1] + u, ep, dev_counter=b["perm_ctr"], out=sh.perm)
                 batches.append(ops.PpoBatch(sh.obs[:T].view(B, D), sh.action.view(B), sh.log_prob.view(B), sh.value.view(B),
                                             sh.advantages.view(B), sh.targets.view(B), sh.adv_stats, sh.perm))
+            # single shard on a single device: the gradient reduction can hand sum(g^2) straight to the fused
+            # optimiser (no separate norm pass / grid barrier); otherwise the all-reduce sits in between.
+            prenorm = precision == ops.STX_PREC_BF16 and U == 1 and world == 1
             for i in range(nmb):  # _update_minibatch (ff_ppo.py:184-284)
-                grads.zero_()
-                for u in range(U):  # vmap over "batch" + pmean("batch") (ff_ppo.py:253-256)
+                for u in range(U):  # vmap over "batch" + pmean("batch") (ff_ppo.py:253-256); first shard overwrites
                     ops.ppo_minibatch_grads(sa, sc, b["arena"], batches[u], i * mb, mb, float(sysc.clip_eps),
                                             float(sysc.ent_coef), float(sysc.vf_coef), bool(sysc.standardize_advantages),
-                                            grads, metrics[ep, i], b["ws"], precision, 1.0 / U, b["arena_bf16"])
+                                            grads, metrics[ep, i], b["ws"], precision, 1.0 / U, b["arena_bf16"],
+                                            overwrite=(u == 0), adam_scratch=b["plan"].scratch if prenorm else None)
                 if world > 1:  # pmean over "device" (ff_ppo.py:258-261): summed here, scaled in K4
                     dist.all_reduce(grads, op=dist.ReduceOp.SUM)
                 # UPDATE ACTOR AND CRITIC PARAMS AND OPTIMISER STATE (ff_ppo.py:264-273), one launch
                 ops.clip_adam_step(b["plan"], b["arena"], grads, a_tree.arena_mu, a_tree.arena_nu,
-                                   grad_scale=1.0 / world, params_bf16=b["arena_bf16"])
+                                   grad_scale=1.0 / world, params_bf16=b["arena_bf16"], prenorm=prenorm)
         if world > 1:
             dist.all_reduce(metrics, op=dist.ReduceOp.SUM)
             metrics.mul_(1.0 / world)

@@ -42,8 +42,8 @@ def test_struct_layouts_match_c():
 
     assert ctypes.sizeof(_lib.StxMlp) == 4 + 5 * 4 + 8 + 8
     assert ctypes.sizeof(_lib.StxAdamSeg) == 24
-    assert ctypes.sizeof(_lib.StxAdamHyper) == 28
-    assert ctypes.sizeof(_lib.StxPpoHyper) == 16
+    assert ctypes.sizeof(_lib.StxAdamHyper) == 32
+    assert ctypes.sizeof(_lib.StxPpoHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoBatch) == 72
 
 
