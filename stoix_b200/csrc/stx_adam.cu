@@ -25,8 +25,8 @@ constexpr int kAdamMaxSegs = 8;
 
 struct AdamScratch {
   unsigned long long arrive;  // monotonically increasing barrier ticket
-  unsigned long long pad;
-  // followed by double partials[kAdamMaxSegs][grid]
+  unsigned long long n_partials;  // PRENORM: block partials per segment, published by the gradient producer
+  // followed by double partials[kAdamMaxSegs][grid]  (PRENORM: [nseg][n_partials])
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(kAdamThreads)
     __shared__ double s_ss;
     if (threadIdx.x < 32) {
       double part = 0.0;
-      const double* vp = partials + (int64_t)s * gridDim.x;
-      for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) part += __ldcg(vp + b);
+      const unsigned int nparts = PRENORM ? (unsigned int)__ldcg(&scratch->n_partials) : gridDim.x;
+      const double* vp = partials + (int64_t)s * nparts;
+      for (unsigned int b = threadIdx.x; b < nparts; b += 32) part += __ldcg(vp + b);
       part = warp_sum(part);
       if (threadIdx.x == 0) s_ss = part;
     }

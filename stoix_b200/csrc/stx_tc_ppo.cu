@@ -664,9 +664,11 @@ struct RedParams {
   float inv_mb;
   int overwrite;
   double* sumsq;             // nullable: [2][gridDim] block partials of sum((weight*g)^2) per optimiser segment
+  unsigned long long* sumsq_count;  // where the number of block partials per segment (= gridDim) is published
 };
 
-constexpr int kRedThreads = 1024;
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 4 * kNumSMs;  // the optimiser scratch holds 8 x 148 doubles = 2 segments x 592 block partials
 
 // Fixed-order reduction of the per-CTA partials into the gradient arena.  One launch, every segment
 // concurrently; 4 independent accumulators per element for load-level parallelism; the association order
@@ -723,6 +725,7 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
       const double b = block_sum<double>(sq[n], sred);
       if (threadIdx.x == 0) p.sumsq[(int64_t)n * gridDim.x + blockIdx.x] = b;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.sumsq_count = gridDim.x;
   }
   if (blockIdx.x == 0 && threadIdx.x < 6) {
     float acc = 0.f;
@@ -886,7 +889,10 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   rp.overwrite = h->overwrite_grads;
   // side output for the fused optimiser: partials[seg][block] right after the 16-byte header of its scratch
   rp.sumsq = (h->overwrite_grads && h->adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->adam_scratch) + 16) : nullptr;
-  tc_reduce_kernel<<<kNumSMs, kRedThreads, 0, st>>>(rp, grad_arena);
+  rp.sumsq_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->adam_scratch) + 8);
+  int red_blocks = (rp.total_items + kRedThreads - 1) / kRedThreads;  // one item per thread, blocks spread over all SMs
+  if (red_blocks > kRedMaxBlocks) red_blocks = kRedMaxBlocks;
+  tc_reduce_kernel<<<red_blocks, kRedThreads, 0, st>>>(rp, grad_arena);
   STX_LAUNCH_OK();
   return STX_OK;
 }
