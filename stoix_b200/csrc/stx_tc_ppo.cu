@@ -667,7 +667,7 @@ struct RedParams {
   unsigned long long* sumsq_count;  // where the number of block partials per segment (= gridDim) is published
 };
 
-constexpr int kRedThreads = 256;
+constexpr int kRedThreads = 288;  // x 592 blocks >= the ~168k gradient entries of the benchmark networks: one element per thread
 constexpr int kRedMaxBlocks = 4 * kNumSMs;  // the optimiser scratch holds 8 x 148 doubles = 2 segments x 592 block partials
 
 // Fixed-order reduction of the per-CTA partials into the gradient arena.  One launch, every segment
@@ -675,54 +675,36 @@ constexpr int kRedMaxBlocks = 4 * kNumSMs;  // the optimiser scratch holds 8 x 1
 // is fixed => run-to-run deterministic gradients.  Optionally leaves the per-block sum of squares of the
 // reduced gradient for the fused optimiser (which can then skip its own norm pass and grid barrier).
 __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
-  double sq[2] = {0.0, 0.0};
+  double sq0 = 0.0, sq1 = 0.0;
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < p.total_items; gi += gridDim.x * blockDim.x) {
     int s = 0, i = gi;
     while (i >= p.seg[s].items) i -= p.seg[s].items, ++s;
     const RedSeg& g = p.seg[s];
-    if (g.vec) {
-      const int cpr = g.cols >> 2;  // float4 items per row
-      const int r = i / cpr, c = (i % cpr) << 2;
-      const float* src = g.part + (int64_t)r * g.src_ld + c;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-      int k = 0;
-      for (; k + 2 <= g.n_part; k += 2) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + (int64_t)k * g.part_stride);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + (int64_t)(k + 1) * g.part_stride);
-        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
-        a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
-      }
-      if (k < g.n_part) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + (int64_t)k * g.part_stride);
-        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
-      }
-      float4 o = make_float4(p.weight * (a0.x + a1.x), p.weight * (a0.y + a1.y), p.weight * (a0.z + a1.z), p.weight * (a0.w + a1.w));
-      float4* dst = reinterpret_cast<float4*>(grad + g.dst_off + (int64_t)r * g.dst_ld + c);
-      if (!p.overwrite) {
-        const float4 old = *dst;
-        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-      }
-      *dst = o;
-      sq[g.net] += (double)o.x * o.x + (double)o.y * o.y + (double)o.z * o.z + (double)o.w * o.w;
-    } else {
+    {
       const int r = i / g.cols, c = i % g.cols;
       const float* src = g.part + (int64_t)r * g.src_ld + c;
-      float a0 = 0.f, a1 = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // many short independent chains: this kernel is latency-bound
       int k = 0;
-      for (; k + 2 <= g.n_part; k += 2) a0 += src[(int64_t)k * g.part_stride], a1 += src[(int64_t)(k + 1) * g.part_stride];
-      if (k < g.n_part) a0 += src[(int64_t)k * g.part_stride];
+      for (; k + 4 <= g.n_part; k += 4) {
+        a0 += src[(int64_t)k * g.part_stride];
+        a1 += src[(int64_t)(k + 1) * g.part_stride];
+        a2 += src[(int64_t)(k + 2) * g.part_stride];
+        a3 += src[(int64_t)(k + 3) * g.part_stride];
+      }
+      for (; k < g.n_part; ++k) a0 += src[(int64_t)k * g.part_stride];
       float* dst = grad + g.dst_off + (g.transpose ? (int64_t)c * g.dst_ld + r : (int64_t)r * g.dst_ld + c);
-      float o = p.weight * (a0 + a1);
+      float o = p.weight * ((a0 + a1) + (a2 + a3));
       if (!p.overwrite) o += *dst;
       *dst = o;
-      sq[g.net] += (double)o * o;
+      if (g.net) sq1 += (double)o * o;
+      else sq0 += (double)o * o;
     }
   }
   if (p.sumsq != nullptr) {  // only meaningful with overwrite (then o is the whole gradient)
     __shared__ double sred[32];
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
-      const double b = block_sum<double>(sq[n], sred);
+      const double b = block_sum<double>(n == 0 ? sq0 : sq1, sred);
       if (threadIdx.x == 0) p.sumsq[(int64_t)n * gridDim.x + blockIdx.x] = b;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.sumsq_count = gridDim.x;
@@ -867,7 +849,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     RedSeg g{};
     g.part = part, g.part_stride = stride, g.n_part = n_part, g.rows = rows, g.cols = cols, g.src_ld = src_ld;
     g.transpose = transpose, g.dst_ld = dst_ld, g.dst_off = dst_off, g.net = net_id;
-    g.vec = (!transpose && cols % 4 == 0 && dst_ld % 4 == 0 && dst_off % 4 == 0 && src_ld % 4 == 0 && stride % 4 == 0) ? 1 : 0;
+    g.vec = 0;  // scalar items: 4x the threads of a float4 version and measurably faster (latency-bound)
     g.items = g.vec ? rows * cols / 4 : rows * cols;
     rp.total_items += g.items;
     rp.seg[sidx++] = g;
