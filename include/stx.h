@@ -207,6 +207,23 @@ int stx_clip_adam_step(float* param_arena, const float* grad_arena, float* mu, f
                        int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper,
                        void* params_bf16, float* gnorm_out, void* scratch, void* stream);
 
+/* C1 fused into K4 -- replaces jax.lax.pmean(axis "device") + both optimiser updates (ff_ppo.py:258-273) in
+ * ONE launch per rank: a one-shot all-reduce by direct loads from every rank's gradient arena over NVLink peer
+ * memory (summed in rank order => identical on all ranks), then global-norm clip + Adam as
+ * stx_clip_adam_step (hyper->grad_scale = 1/world gives the mean).
+ *   peer_grads[r]       HOST array of `world` DEVICE pointers: this call's gradient arena on rank r, peer-mapped
+ *                       into this process (e.g. torch symmetric memory buffer_ptrs).
+ *   peer_signal_pads[r] likewise: a zero-initialised uint32 area per rank; slots [pad_slot_offset .. +world)
+ *                       are used (slot s of rank r's pad is written by rank s with release.sys stores).
+ *   gsum                local fp32 arena receiving the summed gradient.
+ * The caller must alternate between two gradient arenas from one call to the next (ping-pong): together with
+ * the in-kernel handshake this guarantees no arena is rewritten while a peer may still read it.  Every rank
+ * must issue the same sequence of calls.  CUDA-graph capturable (all state is in device memory). */
+int stx_allreduce_clip_adam_step(float* param_arena, const float* const* peer_grads, void* const* peer_signal_pads,
+                                 int world, int rank, int pad_slot_offset, float* gsum, float* mu, float* nu,
+                                 int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper,
+                                 void* params_bf16, float* gnorm_out, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ shuffle -------------------
  * perm[i] = keyed bijection of [0, n) (cycle-walking Feistel over Philox rounds) replacing
  * jax.random.permutation + jnp.take (ff_ppo.py:294-303): the minibatch kernels gather through perm,

@@ -29,6 +29,32 @@ struct AdamScratch {
   // followed by double partials[kAdamMaxSegs][grid]  (PRENORM: [nseg][n_partials])
 };
 
+// ---- C1 fused into K4: one-shot all-reduce over NVLink peer memory ------------------------------------
+// Every rank's gradient arena lives in symmetric (peer-mapped) memory.  Rank r announces "my gradients of
+// call #gen are complete" by writing gen into slot r of every peer's signal pad, waits until all peers
+// announced the same, then each rank sums the W arenas in rank order straight from peer memory (ld.global
+// over NVLink) -- identical association order everywhere => bit-identical parameters on all ranks.  The
+// gradient arenas are ping-ponged by the caller, so this single handshake per call also guarantees that a
+// buffer is not overwritten while a peer may still be reading it.
+struct PeerSync {
+  const float* peer_grads[8];   // this call's gradient arena on every rank (peer-mapped pointers)
+  unsigned int* peer_pads[8];   // signal pads of every rank (slot [rank] is written by that rank)
+  unsigned int* my_pad;
+  unsigned int* local_gen;      // device counter: number of completed calls
+  unsigned int* local_ready;    // released by block 0 once every peer has signalled
+  float* gsum;                  // local arena receiving the summed gradient
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -42,17 +68,60 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
   __syncthreads();
 }
 
-template <bool PRENORM>
+template <bool PRENORM, bool PEER>
 __global__ void __launch_bounds__(kAdamThreads)
-    clip_adam_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ MU,
+    clip_adam_kernel(float* __restrict__ P, const float* G, float* __restrict__ MU,
                      float* __restrict__ NU, int32_t* __restrict__ counts,
                      const StxAdamSeg* __restrict__ segs, int nseg, StxAdamHyper h,
                      __nv_bfloat16* __restrict__ P16, float* __restrict__ gnorm_out,
-                     AdamScratch* scratch) {
+                     AdamScratch* scratch, const PeerSync ps) {
   double* partials = reinterpret_cast<double*>(scratch + 1);
   __shared__ double sred[32];
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
+
+  if (PEER) {
+    // ---- phase 0: cross-rank handshake, then all-reduce by direct peer loads into ps.gsum ----
+    const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(ps.local_gen) + 1u;
+    if (blockIdx.x == 0) {
+      if ((int)threadIdx.x < ps.world) {
+        const int peer = threadIdx.x;
+        __threadfence_system();
+        st_release_sys(ps.peer_pads[peer] + ps.rank, gen);
+        while (ld_acquire_sys(ps.my_pad + peer) < gen) {
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(ps.local_ready) = gen;
+      }
+    } else if (threadIdx.x == 0) {
+      while (*reinterpret_cast<volatile unsigned int*>(ps.local_ready) < gen) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    for (int s = 0; s < nseg; ++s) {
+      const StxAdamSeg seg = segs[s];
+      const int64_t n4 = seg.count / 4;
+      for (int64_t i = gtid; i < n4; i += gthreads) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < ps.world; ++r) {  // fixed rank order on every rank
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.peer_grads[r] + seg.offset) + i);
+          acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(ps.gsum + seg.offset)[i] = acc;
+      }
+      for (int64_t i = n4 * 4 + gtid; i < seg.count; i += gthreads) {
+        float acc = 0.f;
+        for (int r = 0; r < ps.world; ++r) acc += __ldcg(ps.peer_grads[r] + seg.offset + i);
+        ps.gsum[seg.offset + i] = acc;
+      }
+    }
+    __syncthreads();  // this block re-reads only what it wrote (same index mapping in the phases below)
+    G = ps.gsum;
+  }
 
   // ---- phase 1: per-segment sum of squares of (grad * grad_scale) ----
   // (PRENORM: the producer of the gradients already left sum(g^2) partials of the unscaled gradients here)
@@ -78,6 +147,7 @@ __global__ void __launch_bounds__(kAdamThreads)
   for (int s = 0; s < nseg; ++s) cnt[s] = counts[2 * s], sch[s] = counts[2 * s + 1];
 
   if (!PRENORM) grid_barrier(&scratch->arrive);
+  if (PEER && gtid == 0) *ps.local_gen = *ps.local_gen + 1u;  // every block read local_gen before this barrier
 
   // ---- phase 2 ----
   for (int s = 0; s < nseg; ++s) {
@@ -175,7 +245,7 @@ using namespace stx;
 
 extern "C" size_t stx_adam_scratch_bytes(int nseg) {
   (void)nseg;
-  return sizeof(AdamScratch) + sizeof(double) * kAdamMaxSegs * kNumSMs;
+  return sizeof(AdamScratch) + sizeof(double) * kAdamMaxSegs * kNumSMs + 64;  // + peer-sync generation words
 }
 
 // Host-side mirror of the segment table is needed to size the grid: callers pass the total span.
@@ -192,14 +262,15 @@ extern "C" int stx_clip_adam_step(float* param_arena, const float* grad_arena, f
               "stx_clip_adam_step: steps_per_update/num_updates must be positive");
   // The grid is fixed (one wave) so the barrier ticket arithmetic is launch-invariant.
   const int grid = kNumSMs;
+  const PeerSync none{};
   if (hyper->prenorm)
-    clip_adam_kernel<true><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+    clip_adam_kernel<true, false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
         param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
-        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
+        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch), none);
   else
-    clip_adam_kernel<false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+    clip_adam_kernel<false, false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
         param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
-        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch));
+        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch), none);
   STX_LAUNCH_OK();
   (void)adam_grid;
   return STX_OK;
@@ -211,6 +282,36 @@ extern "C" int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  STX_LAUNCH_OK();
+  return STX_OK;
+}
+
+// Fused gradient all-reduce + clip + Adam (one launch per optimiser step on every rank).
+extern "C" int stx_allreduce_clip_adam_step(float* param_arena, const float* const* peer_grads, void* const* peer_signal_pads,
+                                            int world, int rank, int pad_slot_offset, float* gsum, float* mu, float* nu,
+                                            int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper,
+                                            void* params_bf16, float* gnorm_out, void* scratch, void* stream) {
+  STX_REQUIRE(param_arena && peer_grads && peer_signal_pads && gsum && mu && nu && counts && segs && hyper && scratch, STX_E_ARG,
+              "stx_allreduce_clip_adam_step: null pointer");
+  STX_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, STX_E_SHAPE, "stx_allreduce_clip_adam_step: world=%d rank=%d (2..8 ranks)", world, rank);
+  STX_REQUIRE(nseg >= 1 && nseg <= kAdamMaxSegs, STX_E_SHAPE, "stx_allreduce_clip_adam_step: nseg=%d", nseg);
+  STX_REQUIRE(!hyper->prenorm, STX_E_ARG, "stx_allreduce_clip_adam_step: prenorm is a single-device shortcut");
+  PeerSync ps{};
+  for (int r = 0; r < world; ++r) {
+    STX_REQUIRE(peer_grads[r] && peer_signal_pads[r], STX_E_ARG, "stx_allreduce_clip_adam_step: null peer pointer %d", r);
+    ps.peer_grads[r] = peer_grads[r];
+    ps.peer_pads[r] = reinterpret_cast<unsigned int*>(peer_signal_pads[r]) + pad_slot_offset;
+  }
+  ps.my_pad = ps.peer_pads[rank];
+  // local generation / release words live behind the barrier ticket of the optimiser scratch
+  char* sc = reinterpret_cast<char*>(scratch);
+  const size_t base = sizeof(AdamScratch) + sizeof(double) * kAdamMaxSegs * kNumSMs;
+  ps.local_gen = reinterpret_cast<unsigned int*>(sc + base);
+  ps.local_ready = reinterpret_cast<unsigned int*>(sc + base + 8);
+  ps.gsum = gsum, ps.world = world, ps.rank = rank;
+  clip_adam_kernel<false, true><<<kNumSMs, kAdamThreads, 0, (cudaStream_t)stream>>>(
+      param_arena, gsum, mu, nu, counts, segs, nseg, *hyper, reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out,
+      reinterpret_cast<AdamScratch*>(scratch), ps);
   STX_LAUNCH_OK();
   return STX_OK;
 }

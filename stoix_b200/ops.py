@@ -354,6 +354,52 @@ def clip_adam_step(plan: AdamPlan, params: torch.Tensor, grads: torch.Tensor, mu
     )
 
 
+class PeerGradBuffers:
+    """Two gradient arenas in symmetric (peer-mapped) memory + the pointer tables the fused all-reduce/optimiser
+    kernel needs.  torch.distributed._symmetric_memory is plumbing here (allocation + rendezvous of peer
+    pointers); the all-reduce itself is done by stx_allreduce_clip_adam_step with direct NVLink loads."""
+
+    def __init__(self, total: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise StxError("fused all-reduce supports up to 8 ranks (one NVSwitch domain)")
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(int(total), dtype=torch.float32, device=device)
+            t.zero_()
+            self.bufs.append(t)
+            self.handles.append(symm_mem.rendezvous(t, group))
+        h0 = self.handles[0]
+        pad_words = int(h0.signal_pad_size) // 4
+        self.slot = pad_words - 64  # far from the channels torch's own barriers use at the start of the pad
+        pad = h0.get_signal_pad(self.rank, (pad_words,), torch.uint32) if hasattr(h0, "get_signal_pad") else None
+        if pad is not None:
+            pad[self.slot:self.slot + 16] = 0
+        self.grad_ptrs = [(C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in self.handles]
+        self.pad_ptrs = (C.c_void_p * self.world)(*[int(p) for p in h0.signal_pad_ptrs])
+        self.gsum = torch.zeros(int(total), dtype=torch.float32, device=device)
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+
+def allreduce_clip_adam_step(plan: AdamPlan, peers: PeerGradBuffers, which: int, params: torch.Tensor, mu: torch.Tensor,
+                             nu: torch.Tensor, params_bf16: Optional[torch.Tensor] = None) -> None:
+    """Fused mean all-reduce of gradient arena `which` (0/1, ping-pong) + clip + Adam on every rank."""
+    _need_cuda(params, mu, nu, params_bf16)
+    plan.hyper.grad_scale = 1.0 / peers.world
+    plan.hyper.prenorm = 0
+    _lib.check(
+        _lib.load().stx_allreduce_clip_adam_step(_p(params), peers.grad_ptrs[which], peers.pad_ptrs, peers.world, peers.rank, peers.slot,
+                                                 _p(peers.gsum), _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg,
+                                                 C.byref(plan.hyper), _p(params_bf16), _p(plan.gnorm), _p(plan.scratch), _stream()),
+        "stx_allreduce_clip_adam_step",
+    )
+
+
 # ------------------------------------------------------------------------------------------------
 # shuffle / env / misc
 # ------------------------------------------------------------------------------------------------

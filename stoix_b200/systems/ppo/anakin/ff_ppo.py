@@ -146,12 +146,22 @@ def get_learner_fn(
         )
         # optimiser counters live in the learner state (so a checkpointed state carries them)
         plan.counts = a_tree.arena_counts
+        peers = None
+        if world > 1 and bool(arch.get("fused_allreduce", True)) and (epochs * nmb) % 2 == 0 and world <= 8:
+            try:  # gradient arenas in NVLink peer memory: the all-reduce is fused into the optimiser kernel
+                peers = ops.PeerGradBuffers(total, dev)
+            except Exception as e:  # symmetric memory unavailable (no P2P): NCCL all-reduce + K4
+                if rank == 0:
+                    print(f"[stoix_b200] fused all-reduce unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                peers = None
         built.update(
             sa=sa, sc=sc, dev=dev, arena=arena, coff=coff, total=total, shards=shards, plan=plan,
             grads=torch.zeros(total, dtype=torch.float32, device=dev),
             metrics=torch.zeros(epochs, nmb, 8, dtype=torch.float32, device=dev),
             ws=ops.ppo_workspace(sa, sc, mb, precision, dev),
             arena_bf16=getattr(state.params.actor_params, "arena_bf16", None),
+            peers_obj=peers,
+            peers=None,
             roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # categorical call index
             perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # shuffle stream index
             graph=None, eager_done=False,
@@ -235,13 +245,23 @@ def get_learner_fn(
             # single shard on a single device: the gradient reduction can hand sum(g^2) straight to the fused
             # optimiser (no separate norm pass / grid barrier); otherwise the all-reduce sits in between.
             prenorm = precision == ops.STX_PREC_BF16 and U == 1 and world == 1
+            peers = b["peers_obj"]
             for i in range(nmb):  # _update_minibatch (ff_ppo.py:184-284)
+                which = (ep * nmb + i) & 1
+                if peers is not None:
+                    grads = peers.bufs[which]  # ping-pong arenas in peer-mapped memory
                 for u in range(U):  # vmap over "batch" + pmean("batch") (ff_ppo.py:253-256); first shard overwrites
                     ops.ppo_minibatch_grads(sa, sc, b["arena"], batches[u], i * mb, mb, float(sysc.clip_eps),
                                             float(sysc.ent_coef), float(sysc.vf_coef), bool(sysc.standardize_advantages),
                                             grads, metrics[ep, i], b["ws"], precision, 1.0 / U, b["arena_bf16"],
                                             overwrite=(u == 0), adam_scratch=b["plan"].scratch if prenorm else None)
-                if world > 1:  # pmean over "device" (ff_ppo.py:258-261): summed here, scaled in K4
+                if peers is not None:
+                    # pmean over "device" (ff_ppo.py:258-261) + both optimiser updates (:264-273) in ONE launch:
+                    # one-shot all-reduce by direct NVLink peer loads fused into clip+Adam
+                    ops.allreduce_clip_adam_step(b["plan"], peers, which, b["arena"], a_tree.arena_mu, a_tree.arena_nu,
+                                                 params_bf16=b["arena_bf16"])
+                    continue
+                if world > 1:  # pmean over "device": summed by NCCL here, scaled in K4
                     dist.all_reduce(grads, op=dist.ReduceOp.SUM)
                 # UPDATE ACTOR AND CRITIC PARAMS AND OPTIMISER STATE (ff_ppo.py:264-273), one launch
                 ops.clip_adam_step(b["plan"], b["arena"], grads, a_tree.arena_mu, a_tree.arena_nu,

@@ -22,11 +22,11 @@ from stoix_b200.config import compose
 from stoix_b200.systems.ppo.anakin import ff_ppo
 from stoix_b200.utils import make_env
 from stoix_b200.utils.total_timestep_checker import check_total_timesteps
-precision = sys.argv[1]
+precision, fused = sys.argv[1], sys.argv[2]
 E, T = 256, 16
 cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E * world}", f"system.rollout_length={T}",
                                  "system.num_minibatches=4", f"arch.total_timesteps={E * world * T * 4}", "arch.num_evaluation=1",
-                                 f"arch.precision={precision}", "logger.use_console=False"])
+                                 f"arch.precision={precision}", f"arch.fused_allreduce={fused}", "logger.use_console=False"])
 cfg.num_devices, cfg.rank = world, rank
 cfg = check_total_timesteps(cfg, quiet=True)
 env, _ = make_env.make(cfg)
@@ -46,20 +46,21 @@ dist.all_gather(sums, obs_sum)
 if rank == 0:
     same = all(torch.equal(gathered[0], g) for g in gathered)
     print(json.dumps({"params_identical_across_ranks": same, "changed": not torch.equal(p0, arena), "finite": bool(torch.isfinite(arena).all()),
-                      "shards_differ": len({float(s) for s in sums}) == world,
+                      "shards_differ": len({float(s) for s in sums}) == world, "fused_used": learn.built["peers_obj"] is not None,
+                      "arena_sum": float(arena.double().sum()),
                       "value_loss": float(out.train_metrics["value_loss"].mean())}))
 dist.barrier(); torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)  # NCCL teardown can hang at exit here
 '''
 
 
-@pytest.mark.parametrize("precision", ["f32", "bf16"])
-def test_two_rank_update_keeps_replicas_identical(precision, tmp_path):
+@pytest.mark.parametrize("precision,fused", [("f32", "False"), ("bf16", "False"), ("bf16", "True"), ("f32", "True")])
+def test_two_rank_update_keeps_replicas_identical(precision, fused, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29511", str(script), precision]
+           "--master-port", "29511", str(script), precision, fused]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     import json
@@ -67,3 +68,5 @@ def test_two_rank_update_keeps_replicas_identical(precision, tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["params_identical_across_ranks"] and res["changed"] and res["finite"] and res["shards_differ"], res
+    assert res["fused_used"] == (fused == "True"), res
+    print(res)
