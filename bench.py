@@ -244,6 +244,7 @@ def run_ours(args):
         f"arch.total_num_envs={E_PER_GPU * world}", f"system.rollout_length={T}", f"system.epochs={EPOCHS}",
         f"system.num_minibatches={NMB}", f"arch.total_timesteps={E_PER_GPU * world * T * total_updates}",
         "arch.num_evaluation=1", f"arch.precision={precision}", "logger.use_console=False",
+        f"arch.fused_allreduce={not args.nccl_allreduce}",
     ])
     cfg.num_devices, cfg.rank = world, rank
     cfg = check_total_timesteps(cfg, quiet=True)
@@ -364,6 +365,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "env_steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": dt_e2e / args.steps * 1e3},
             "gpu_launches": int(launches_per_update * args.steps), "launches_per_step": int(launches_per_update),
+            "allreduce": ("none" if world == 1 else ("fused NVLink one-shot all-reduce inside the optimiser kernel" if learn.built.get("peers_obj") is not None else "NCCL all-reduce")),
             "clocks": clocks, "roofline": roofline, "gae_roofline": gae_roof, "phase_ms": phase_ms,
             "tensor_roofline_env_steps_per_s_per_gpu": peaks["bf16_tflops_sustained"] * 1e12 / sum(flops_per_env_step()),
         }
@@ -387,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("STX_BENCH_PRECISION", "bf16"), choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + K4 instead of the fused NVLink all-reduce/optimiser kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
