@@ -217,6 +217,12 @@ def _one_minibatch(model, tr, perm, i, mb):
 
 # ----------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # Libraries (NCCL prints its version banner on stdout) must not pollute the ONE JSON line: everything
+    # written to fd 1 during the run goes to stderr; the JSON line is written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -371,7 +377,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     sys.stdout.flush()
     if world > 1:
         dist.barrier()
