@@ -17,9 +17,7 @@
 namespace stx {
 namespace {
 
-constexpr int kL = 4;        // timesteps per thread
 constexpr int kChunks = 32;  // chunk lanes per block == warp width (suffix scan by shuffles)
-constexpr int kSeg = kL * kChunks;
 
 struct PpoIn {  // exactly what ff_ppo.py:164-169 feeds
   const float *reward, *v_tm1, *v_t;
@@ -78,12 +76,13 @@ struct GenericIn {  // float discount / lambda / truncation arrays (multistep.py
   }
 };
 
-template <class In, int VEC, int QUADS>
+template <class In, int VEC, int QUADS, int kL = 4>
 __global__ void __launch_bounds__(QUADS* kChunks)
     gae_scan_kernel(In in, int T, int E, float* __restrict__ adv, float* __restrict__ tgt,
                     int want_stats, double2* __restrict__ partials, unsigned int* counter,
                     float* __restrict__ stats) {
   constexpr int ENVS = QUADS * VEC;  // envs per block
+  constexpr int kSeg = kL * kChunks;  // timesteps covered per pass over the block
   const int q = threadIdx.x % QUADS, chunk = threadIdx.x / QUADS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e0 = (blockIdx.x * QUADS + q) * VEC;
@@ -211,7 +210,16 @@ int launch_gae(const In& in, int T, int E, bool vec4, int standardize, float* ad
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double2* partials = reinterpret_cast<double2*>(reinterpret_cast<char*>(scratch) + 16);
   const int want = standardize != 0;
-  if (vec4 && g_quads_override / 100 == 2) {  // experimental float2 variants: tuning code 2xx
+  if (vec4 && g_quads_override / 100 == 3) {  // L = 2 timesteps per thread (fewer registers, more resident blocks): code 3xx
+    const int quads = g_quads_override % 100, total = E / 4;
+    const int grid = (total + quads - 1) / quads;
+    if (quads == 32)
+      gae_scan_kernel<In, 4, 32, 2><<<grid, 32 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else if (quads == 16)
+      gae_scan_kernel<In, 4, 16, 2><<<grid, 16 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else
+      gae_scan_kernel<In, 4, 8, 2><<<grid, 8 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+  } else if (vec4 && g_quads_override / 100 == 2) {  // experimental float2 variants: tuning code 2xx
     const int groups = g_quads_override % 100, total = E / 2;
     const int grid = (total + groups - 1) / groups;
     if (groups == 32)

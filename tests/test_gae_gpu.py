@@ -101,7 +101,7 @@ def test_generic_form_array_lambda_and_truncation():
     np.testing.assert_allclose(tgt.cpu().numpy(), tgt_o, rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("quads", [2, 4, 8, 16, 32, 216, 232])
+@pytest.mark.parametrize("quads", [2, 4, 8, 16, 32, 216, 232, 308, 316, 332])
 def test_every_block_shape_agrees(quads):
     import ctypes
 
