@@ -118,8 +118,12 @@ def test_every_block_shape_agrees(quads):
         a1, t1, s1 = ops.gae_ppo(*args)
     finally:
         lib.stx_gae_set_tuning(0)
-    assert torch.equal(a0, a1) and torch.equal(t0, t1)
-    np.testing.assert_allclose(s0.cpu().numpy(), s1.cpu().numpy(), rtol=1e-6)
+    if quads < 300:  # same 4-step chunking -> same float association -> bit-identical
+        assert torch.equal(a0, a1) and torch.equal(t0, t1)
+    else:            # 2-step chunking re-associates the affine composition: equal to fp32 rounding
+        np.testing.assert_allclose(a0.cpu().numpy(), a1.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(t0.cpu().numpy(), t1.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(s0.cpu().numpy(), s1.cpu().numpy(), rtol=1e-5)
 
 
 def test_full_size_properties():
