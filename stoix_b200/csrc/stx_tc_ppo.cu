@@ -335,29 +335,35 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         const float* bias = layer == 0 ? s_b0 : s_b1;
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
         __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
-#pragma unroll 1
+        uint32_t pk[kFbChunksPerWarp][16];
+#pragma unroll
         for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
           const int c = sub * kFbChunksPerWarp + cc;
-          uint32_t r[32], pk[16];
+          uint32_t r[32];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
             const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
-            pk[j] = pack_bf16(v0, v1);
+            pk[cc][j] = pack_bf16(v0, v1);
           }
-          tmem_st16(ta + c * 16, pk);
-          if (!(p.dbg_skip & 1)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
-              *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          tmem_st16(ta + c * 16, pk[cc]);
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
+        // off the critical path: the tiled global copy for K3b is issued while the next GEMM runs
+        if (!(p.dbg_skip & 1)) {
+#pragma unroll
+          for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
+            const int c = sub * kFbChunksPerWarp + cc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
+              *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[cc][4 * j], pk[cc][4 * j + 1], pk[cc][4 * j + 2], pk[cc][4 * j + 3]);
+          }
+        }
       }
       // ---------------- E2: head + loss + d(head) ----------------
       if (warp == kFbEpiWarp0) STX_STAMP(20);
@@ -470,7 +476,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
         __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
-#pragma unroll 1
+        uint32_t pk[kFbChunksPerWarp][16];
+#pragma unroll
         for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
           const int c = sub * kFbChunksPerWarp + cc;
           uint32_t r[32], hm[16];
@@ -482,17 +489,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           for (int j = 0; j < 16; ++j) {
             if ((hm[j] & 0x7FFFu) == 0u) r[2 * j] = 0u;
             if ((hm[j] & 0x7FFF0000u) == 0u) r[2 * j + 1] = 0u;
+            pk[cc][j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           }
-          // bf16 pack 8 columns at a time: A operand of the next GEMM (dh2 only) + tiled global copy
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              pk[j] = pack_bf16(__uint_as_float(r[8 * g4 + 2 * j]), __uint_as_float(r[8 * g4 + 2 * j + 1]));
-            if (layer == 1) tmem_st4(ta + c * 16 + g4 * 4, pk);  // dh2 replaces h2 as the A operand of G4
-            if (!(p.dbg_skip & 1)) *tiled_ptr(dout, mrow, c * 4 + g4, 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+          if (layer == 1) tmem_st16(ta + c * 16, pk[cc]);  // dh2 replaces h2 as the A operand of G4
           if (!(p.dbg_skip & 2)) {  // bias gradient: column sums over this warp's 32 rows (fp32, before rounding)
             float dv[32];
 #pragma unroll
@@ -506,6 +505,15 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
         if (warp == kFbEpiWarp0) STX_STAMP(26 + (1 - layer));
+        if (!(p.dbg_skip & 1)) {  // tiled global copies after the hand-off: they overlap the next GEMM
+#pragma unroll
+          for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
+            const int c = sub * kFbChunksPerWarp + cc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[cc][4 * j], pk[cc][4 * j + 1], pk[cc][4 * j + 2], pk[cc][4 * j + 3]);
+          }
+        }
       }
     }
   }
