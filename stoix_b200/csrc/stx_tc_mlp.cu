@@ -10,8 +10,8 @@
 //   A1 (TMEM, packed bf16) --tcgen05.mma TS (A from TMEM)--> D1 --epilogue--> A2 --TS--> D2 --> +b2 -> HBM
 //
 // so hidden activations never leave the SM (SURVEY.md 7 "Keeping activations out of HBM").
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
-// allocator, warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one row per thread).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
+// allocator, warps 2-17 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one row per thread, 2 column chunks).
 // Operand layouts: X K-major SW128; W0/W1 row-major (in,out) loaded by TMA as [rows x 64-col] blocks =
 // MN-major SW128 B operands (the same image serves as the K-major B operand of the backward pass);
 // W2 (256 x A<=16) is staged by hand in the un-swizzled core-matrix layout.
@@ -27,7 +27,9 @@ namespace tc {
 constexpr int kTileM = 128;
 constexpr int kH = 256;
 constexpr int kXStages = 2;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: hides the tcgen05.ld / pack latencies
+constexpr int kChunksPerWarp = 8 / (kEpiWarps / 4);
+constexpr int kThreads = 32 * (2 + kEpiWarps);  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 // shared-memory map (bytes from a 1024-aligned base)
 constexpr uint32_t kOffW1 = 0;                         // 4 x [256 rows x 128 B]
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     mbar_init(w_full, 1);
     mbar_init(mma_done, 1);
-    mbar_init(epi_done, 4);
+    mbar_init(epi_done, kEpiWarps);
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW0);
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;
+    // ===================== epilogue warps: lane quarter q = warp % 4, `sub` picks the column chunks =============
+    const int q = warp & 3, sub = (warp - 2) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tmem_d = tmem + lane_addr, tmem_a = tmem + lane_addr + 256;
     for (int it = 0; it < my_tiles; ++it) {
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float* bias = layer == 0 ? s_b0 : s_b1;
         float* dbg = layer == 0 ? p.dbg_h1 : p.dbg_h2;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+          const int c = sub * kChunksPerWarp + cc;
           uint32_t r[32], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -209,10 +212,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
       }
-      // head
+      // head (one row per thread: the sub == 0 warps)
       mbar_wait(mma_done, (g0 + 2) & 1, 9);
       tc_fence_after();
-      {
+      if (sub == 0) {
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
