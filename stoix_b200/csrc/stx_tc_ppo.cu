@@ -41,12 +41,8 @@ __device__ long long* g_clock_buf = nullptr;
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;
-constexpr int kFbEpiWarps = 16;  // 4 per lane quarter (and per SM sub-partition): enough warps to hide the shuffle / TMEM latencies
-constexpr int kFbProdWarps = 2;  // gather producers: 64 threads, two rows each
-constexpr int kFbEpiWarp0 = kFbProdWarps + 1;
-constexpr int kFbChunksPerWarp = 8 / (kFbEpiWarps / 4);
-constexpr int kFbThreads = 32 * (kFbEpiWarp0 + kFbEpiWarps);  // warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5.. epilogue
-constexpr int kFbMmaWarp = kFbProdWarps;
+constexpr int kFbThreads = 416;  // warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5..12 epilogue
+constexpr int kFbMmaWarp = 4;
 
 // ---- K3a shared-memory map ------------------------------------------------------------------------
 constexpr uint32_t kOffW1 = 0;
@@ -138,12 +134,12 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], kFbProdWarps);  // one arrival per producer warp
+      mbar_init(&x_full[s], 4);  // one arrival per producer warp
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(w_full, 1);
     mbar_init(mma_done, 1);
-    mbar_init(epi_done, kFbEpiWarps);
+    mbar_init(epi_done, 8);
     fence_barrier_init();
     tma_prefetch_desc(tmW0);
     tma_prefetch_desc(tmW1);
@@ -180,41 +176,33 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 
   float m_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actor_loss, entropy, value_loss, adv, pred value, target
 
-  if (warp < kFbProdWarps) {
-    // ===================== producers: weights by TMA, X rows gathered (two rows per thread) =====================
+  if (warp < 4) {
+    // ===================== producers: weights by TMA, X rows gathered one row per thread =====================
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(w_full, 32768 + 131072);
       for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
       for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
     }
     const int dchunks = p.D >> 3;  // 16-byte chunks per observation row
+    const int r = threadIdx.x;     // row of the tile owned by this thread
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       const int tile = cta_in_net + it * ncta;
-      uint4 v[2][8];
-      int64_t mrow[2];
+      const int64_t mrow = (int64_t)tile * kTileM + r;
+      const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+      uint4 v[8];
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int r = threadIdx.x + h2 * 64;
-        mrow[h2] = (int64_t)tile * kTileM + r;
-        const int64_t src = p.idx ? (int64_t)p.idx[mrow[h2]] : p.row0 + mrow[h2];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)  // independent 16-byte loads, all in flight together
-          v[h2][c] = c < dchunks ? *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int c = 0; c < 8; ++c)  // 8 independent 16-byte loads in flight per thread
+        v[c] = c < dchunks ? *reinterpret_cast<const uint4*>(p.obs + src * p.D + c * 8) : make_uint4(0u, 0u, 0u, 0u);
       if (warp == 0) STX_STAMP(48);
       if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) & 1) ^ 1, 1);
       if (warp == 0) STX_STAMP(49);
+      uint8_t* xs = smem + kOffX + s * 16384 + r * 128;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int r = threadIdx.x + h2 * 64;
-        uint8_t* xs = smem + kOffX + s * 16384 + r * 128;
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
+      if (which == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[h2][c];  // Swizzle<3,4,3>
-        if (which == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) *tiled_ptr(p.xg, mrow[h2], c, 8) = v[h2][c];
-        }
+        for (int c = 0; c < 8; ++c) *tiled_ptr(p.xg, mrow, c, 8) = v[c];
       }
       if (warp == 0) STX_STAMP(50);
       fence_async_proxy();
@@ -293,10 +281,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       __syncwarp();
     }
   } else {
-    // ===================== epilogue warps: lane quarter q = warp % 4; `sub` selects this warp's column chunks; the
-    // sub == 0 warps also run the head/loss epilogue (one row per thread needs all 16 head columns) ==========
-    const int q = warp & 3, sub = (warp - kFbEpiWarp0) >> 2;
-    const int half = sub == 0 ? 0 : 1;  // 'half == 0' marks the warps that own E2
+    // ===================== epilogue warps 5..12: lane quarter q = warp % 4, column half `half` =====================
+    const int q = warp & 3, half = (warp - 5) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
     const float inv_m = 1.0f / (float)p.mb;
@@ -328,53 +314,47 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       // ---------------- E0 / E1: hidden layers ----------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        if (warp == kFbEpiWarp0) STX_STAMP(16 + 2 * layer);
+        if (warp == 5) STX_STAMP(16 + 2 * layer);
         mbar_wait(mma_done, (g0 + layer) & 1, 10 + layer);
         tc_fence_after();
-        if (warp == kFbEpiWarp0) STX_STAMP(17 + 2 * layer);
+        if (warp == 5) STX_STAMP(17 + 2 * layer);
         const float* bias = layer == 0 ? s_b0 : s_b1;
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
         __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
-        uint32_t pk[kFbChunksPerWarp][16];
-#pragma unroll
-        for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
-          const int c = sub * kFbChunksPerWarp + cc;
-          uint32_t r[32];
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half * 4 + cc;
+          uint32_t r[32], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
             const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
-            pk[cc][j] = pack_bf16(v0, v1);
+            pk[j] = pack_bf16(v0, v1);
           }
-          tmem_st16(ta + c * 16, pk[cc]);
+          tmem_st16(ta + c * 16, pk);
+          if (!(p.dbg_skip & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
+              *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
-        // off the critical path: the tiled global copy for K3b is issued while the next GEMM runs
-        if (!(p.dbg_skip & 1)) {
-#pragma unroll
-          for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
-            const int c = sub * kFbChunksPerWarp + cc;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
-              *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[cc][4 * j], pk[cc][4 * j + 1], pk[cc][4 * j + 2], pk[cc][4 * j + 3]);
-          }
-        }
       }
       // ---------------- E2: head + loss + d(head) ----------------
-      if (warp == kFbEpiWarp0) STX_STAMP(20);
+      if (warp == 5) STX_STAMP(20);
       mbar_wait(mma_done, (g0 + 2) & 1, 12);
       tc_fence_after();
-      if (warp == kFbEpiWarp0) STX_STAMP(21);
+      if (warp == 5) STX_STAMP(21);
       if (half == 0) {
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
-        if (warp == kFbEpiWarp0) STX_STAMP(40);
+        if (warp == 5) STX_STAMP(40);
         float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dz[j] = 0.f;
@@ -429,7 +409,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           dz[0] = p.vf_coef * dv * inv_m;
           m_acc[2] += 0.5f * fmaxf(q1, q2), m_acc[4] += v, m_acc[5] += tg;
         }
-        if (warp == kFbEpiWarp0) STX_STAMP(41);
+        if (warp == 5) STX_STAMP(41);
         // bias gradient of the head: column sums over the 32 rows of this warp (16 columns)
         {
           // 16 columns: fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
@@ -448,7 +428,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           }
           if (lane < 16) s_db[q * 528 + 512 + lane] += t[0];  // lanes 0..15 hold columns 0..15
         }
-        if (warp == kFbEpiWarp0) STX_STAMP(42);
+        if (warp == 5) STX_STAMP(42);
         // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
         uint32_t pk[8];
 #pragma unroll
@@ -459,9 +439,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
         *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (warp == kFbEpiWarp0) STX_STAMP(43);
+        if (warp == 5) STX_STAMP(43);
         fence_async_proxy();
-        if (warp == kFbEpiWarp0) STX_STAMP(44);
+        if (warp == 5) STX_STAMP(44);
       }
       tc_fence_before();
       __syncwarp();
@@ -469,33 +449,36 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       // ---------------- E3 / E4: dh2 = D * (h2 > 0) ; dh1 = D * (h1 > 0) ----------------
 #pragma unroll 1
       for (int layer = 1; layer >= 0; --layer) {
-        if (warp == kFbEpiWarp0) STX_STAMP(22 + 2 * (1 - layer));
+        if (warp == 5) STX_STAMP(22 + 2 * (1 - layer));
         mbar_wait(mma_done, (g0 + 3 + (1 - layer)) & 1, 13 + layer);
         tc_fence_after();
-        if (warp == kFbEpiWarp0) STX_STAMP(23 + 2 * (1 - layer));
+        if (warp == 5) STX_STAMP(23 + 2 * (1 - layer));
         const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
         __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
-        uint32_t pk[kFbChunksPerWarp][16];
-#pragma unroll
-        for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
-          const int c = sub * kFbChunksPerWarp + cc;
-          uint32_t r[32], hm[16];
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half * 4 + cc;
+          uint32_t r[32], hm[16], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld16(ta + c * 16, hm);
           tmem_ld_wait();
-          // relu mask in place: h is post-relu (>= 0), positive <=> bf16 bit pattern non-zero
+          float dv[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if ((hm[j] & 0x7FFFu) == 0u) r[2 * j] = 0u;
-            if ((hm[j] & 0x7FFF0000u) == 0u) r[2 * j + 1] = 0u;
-            pk[cc][j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            // h is post-relu (>= 0): positive <=> bf16 bit pattern non-zero (and not -0)
+            const bool p0 = (hm[j] & 0x7FFFu) != 0u, p1 = (hm[j] & 0x7FFF0000u) != 0u;
+            dv[2 * j] = p0 ? __uint_as_float(r[2 * j]) : 0.f;
+            dv[2 * j + 1] = p1 ? __uint_as_float(r[2 * j + 1]) : 0.f;
+            pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
           }
-          if (layer == 1) tmem_st16(ta + c * 16, pk[cc]);  // dh2 replaces h2 as the A operand of G4
-          if (!(p.dbg_skip & 2)) {  // bias gradient: column sums over this warp's 32 rows (fp32, before rounding)
-            float dv[32];
+          if (layer == 1) tmem_st16(ta + c * 16, pk);  // dh2 replaces h2 as the A operand of G4
+          if (!(p.dbg_skip & 1)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dv[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 4; ++j)
+              *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (!(p.dbg_skip & 2)) {
             const float cs = warp_colsum32(dv, lane);
             dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
           }
@@ -504,16 +487,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(epi_done);
-        if (warp == kFbEpiWarp0) STX_STAMP(26 + (1 - layer));
-        if (!(p.dbg_skip & 1)) {  // tiled global copies after the hand-off: they overlap the next GEMM
-#pragma unroll
-          for (int cc = 0; cc < kFbChunksPerWarp; ++cc) {
-            const int c = sub * kFbChunksPerWarp + cc;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[cc][4 * j], pk[cc][4 * j + 1], pk[cc][4 * j + 2], pk[cc][4 * j + 3]);
-          }
-        }
+        if (warp == 5) STX_STAMP(26 + (1 - layer));
       }
     }
   }
