@@ -1,4 +1,4 @@
-"""Times the K3 launches alone (CUDA events) for profiling experiments (STX_DEBUG_SKIP bits)."""
+"""Times the K3 launches alone (CUDA events)."""
 import sys
 import torch
 sys.path.insert(0, ".")

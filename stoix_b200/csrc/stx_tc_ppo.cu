@@ -20,7 +20,6 @@
 //  tc_reduce_kernel     fixed-order reduction of the per-CTA partials into the flat fp32 gradient arena
 //      (deterministic; also the bias gradients and the six loss metrics).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "stx_common.cuh"
 #include "stx_tc_ptx.cuh"
@@ -78,7 +77,6 @@ struct FbParams {
   int D;
   int mb;
   float clip_eps, ent_coef, vf_coef;
-  int dbg_skip;  // profiling experiments only (env STX_DEBUG_SKIP): bit0 = skip activation stores, bit1 = skip bias butterflies
 };
 
 // Tiled activation layout shared by K3a (writer) and K3b (reader): element (row, col) of a [mb x 8*CG]
@@ -334,11 +332,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             pk[j] = pack_bf16(v0, v1);
           }
           tmem_st16(ta + c * 16, pk);
-          if (!(p.dbg_skip & 1)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
-              *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
+            *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -473,15 +469,11 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
           }
           if (layer == 1) tmem_st16(ta + c * 16, pk);  // dh2 replaces h2 as the A operand of G4
-          if (!(p.dbg_skip & 1)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-          if (!(p.dbg_skip & 2)) {
-            const float cs = warp_colsum32(dv, lane);
-            dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
-          }
+          for (int j = 0; j < 4; ++j)
+            *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          const float cs = warp_colsum32(dv, lane);
+          dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
         }
         if (layer == 1) tmem_st_wait();
         tc_fence_before();
@@ -813,11 +805,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   fp.adv_stats = h->standardize_advantages ? b->adv_stats : nullptr;
   fp.metric_part = ws.metric_part;
   fp.D = D, fp.mb = (int)mb, fp.clip_eps = h->clip_eps, fp.ent_coef = h->ent_coef, fp.vf_coef = h->vf_coef;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("STX_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
-    fp.dbg_skip = dbg;
-  }
+
   static bool attr_set = false;
   if (!attr_set) {
     STX_CUDA_OK(cudaFuncSetAttribute(tc_ppo_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbSmemBytes));
