@@ -25,10 +25,12 @@ for i in range(4):
 torch.cuda.synchronize()
 c = clk.cpu().tolist()
 base = min(x for x in c if x > 0)
-names = {0: "mma: tile start", 1: "mma: x_full+prev E4 ok -> issue G0", 2: "mma: G0 issued, wait E0", 3: "mma: E0 done -> issue G1", 4: "mma: wait E1",
-         5: "mma: E1 done -> issue G2", 6: "mma: wait E2", 7: "mma: E2 done -> issue G3", 8: "mma: wait E3", 9: "mma: E3 done -> issue G4",
-         16: "epi: wait G0", 17: "epi: G0 done", 18: "epi: wait G1 (E0 finished)", 19: "epi: G1 done", 20: "epi: wait G2 (E1 finished)", 21: "epi: G2 done",
-         22: "epi: wait G3 (E2 finished)", 40: "E2: logits loaded", 41: "E2: loss math done", 42: "E2: butterfly done", 43: "E2: stores issued", 44: "E2: fence.proxy.async done", 48: "prod: loads issued (tile 1)", 49: "prod: x_empty ok", 50: "prod: smem+xg stores issued", 51: "prod: fence done", 23: "epi: G3 done", 24: "epi: wait G4 (E3 finished)", 25: "epi: G4 done", 26: "epi: E3 arrive", 27: "epi: E4 arrive"}
+names = {0: "mma: tile start", 1: "mma: G0 issued (all parts)", 3: "mma: G1 issued (E0 finished)", 5: "mma: G2 issued (E1 finished)",
+         7: "mma: G3 issued (E2 finished)", 9: "mma: G4 issued (E3 finished)",
+         16: "epi: E0 start", 17: "epi: G0 part 0 ready", 18: "epi: E1 start", 19: "epi: G1 part 0 ready", 20: "epi: E2 start (E1 finished)",
+         21: "epi: head ready", 41: "E2: loss math done", 44: "E2: dz in smem, head_done arrived", 22: "epi: E3 start", 24: "epi: E4 start",
+         26: "epi: E3 finished", 27: "epi: E4 finished", 48: "prod: loads issued (tile 1)", 49: "prod: x_empty ok", 50: "prod: smem+xg stores issued",
+         51: "prod: fence done"}
 for k in sorted(names, key=lambda k: c[k]):
     if c[k] > 0:
         print(f"{c[k] - base:8d} cyc  {names[k]}")

@@ -76,9 +76,14 @@ __global__ void __launch_bounds__(kAdamThreads)
                      __nv_bfloat16* __restrict__ P16, float* __restrict__ gnorm_out,
                      AdamScratch* scratch, const PeerSync ps) {
   double* partials = reinterpret_cast<double*>(scratch + 1);
+  unsigned long long* finish = reinterpret_cast<unsigned long long*>(partials + kAdamMaxSegs * kNumSMs) + 2;  // after the peer words
   __shared__ double sred[32];
+  __shared__ StxAdamSeg s_seg[kAdamMaxSegs];
+  __shared__ float s_gs[kAdamMaxSegs], s_bc1[kAdamMaxSegs], s_bc2[kAdamMaxSegs], s_lr[kAdamMaxSegs], s_gn[kAdamMaxSegs];
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
+  if ((int)threadIdx.x < nseg) s_seg[threadIdx.x] = segs[threadIdx.x];
+  __syncthreads();
 
   if (PEER) {
     // ---- phase 0: cross-rank handshake, then all-reduce by direct peer loads into ps.gsum ----
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kAdamThreads)
     }
     __syncthreads();
     for (int s = 0; s < nseg; ++s) {
-      const StxAdamSeg seg = segs[s];
+      const StxAdamSeg seg = s_seg[s];
       const int64_t n4 = seg.count / 4;
       for (int64_t i = gtid; i < n4; i += gthreads) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(kAdamThreads)
   // ---- phase 1: per-segment sum of squares of (grad * grad_scale) ----
   // (PRENORM: the producer of the gradients already left sum(g^2) partials of the unscaled gradients here)
   for (int s = 0; s < nseg && !PRENORM; ++s) {
-    const StxAdamSeg seg = segs[s];
+    const StxAdamSeg seg = s_seg[s];
     const float4* g4 = reinterpret_cast<const float4*>(G + seg.offset);
     const int64_t n4 = seg.count / 4;
     float acc = 0.f;
@@ -142,52 +147,72 @@ __global__ void __launch_bounds__(kAdamThreads)
     const double bs = block_sum<double>((double)acc, sred);
     if (threadIdx.x == 0) partials[(int64_t)s * gridDim.x + blockIdx.x] = bs;
   }
-  // counts are read before the barrier and written (by block 0) after it: no intra-launch race.
-  int32_t cnt[kAdamMaxSegs], sch[kAdamMaxSegs];
-  for (int s = 0; s < nseg; ++s) cnt[s] = counts[2 * s], sch[s] = counts[2 * s + 1];
-
   if (!PRENORM) grid_barrier(&scratch->arrive);
   if (PEER && gtid == 0) *ps.local_gen = *ps.local_gen + 1u;  // every block read local_gen before this barrier
 
   // ---- phase 2 ----
+  // PRENORM: the gradients are final at kernel entry, so the first item of the first two segments is requested
+  // BEFORE the norm reduction: its loads overlap the (dependent) partials round trip.
+  constexpr int kPf = 2;
+  float4 pf_g[kPf], pf_m[kPf], pf_v[kPf], pf_p[kPf];
+  if (PRENORM) {
+#pragma unroll
+    for (int s = 0; s < kPf; ++s)
+      if (s < nseg && gtid < s_seg[s].count / 4) {
+        const int64_t o = s_seg[s].offset;
+        pf_g[s] = reinterpret_cast<const float4*>(G + o)[gtid];
+        pf_m[s] = reinterpret_cast<const float4*>(MU + o)[gtid];
+        pf_v[s] = reinterpret_cast<const float4*>(NU + o)[gtid];
+        pf_p[s] = reinterpret_cast<const float4*>(P + o)[gtid];
+      }
+  }
+  // every block re-reduces the per-block partials in the same fixed order (warp s <-> segment s: lane-strided
+  // loads, xor-butterfly) and lane 0 derives the segment's scalars once for the whole block
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < nseg) {
+    const int s = warp;
+    const unsigned int nparts = PRENORM ? (unsigned int)__ldcg(&scratch->n_partials) : gridDim.x;
+    const double* vp = partials + (int64_t)s * nparts;
+    double part = 0.0;
+    for (unsigned int b = lane; b < nparts; b += 32) part += __ldcg(vp + b);
+    part = warp_sum(part);
+    if (lane == 0) {
+      const double ss = PRENORM ? part * (double)h.grad_scale * (double)h.grad_scale : part;
+      const float g_norm = (float)sqrt(ss);
+      // optax.clip_by_global_norm: trigger = g_norm < max_norm
+      const float clip = (g_norm < s_seg[s].max_grad_norm) ? 1.0f : s_seg[s].max_grad_norm / g_norm;
+      const int32_t c = counts[2 * s] + 1;
+      float lr = s_seg[s].init_lr;
+      if (h.decay) {
+        const int32_t k = counts[2 * s + 1] / h.steps_per_update;  // floor division, utils/training.py:25
+        lr = s_seg[s].init_lr * (1.0f - (float)k / (float)h.num_updates);
+      }
+      s_gs[s] = h.grad_scale * clip;
+      s_bc1[s] = 1.0f - powf(h.b1, (float)c);
+      s_bc2[s] = 1.0f - powf(h.b2, (float)c);
+      s_lr[s] = lr;
+      s_gn[s] = g_norm;
+    }
+  }
+  __syncthreads();
+  const float ob1 = 1.0f - h.b1, ob2 = 1.0f - h.b2;
   for (int s = 0; s < nseg; ++s) {
-    const StxAdamSeg seg = segs[s];
-    // every block re-reduces the per-block partials in the same fixed order (warp 0: lane-strided loads,
-    // xor-butterfly) and broadcasts through shared memory
-    __shared__ double s_ss;
-    if (threadIdx.x < 32) {
-      double part = 0.0;
-      const unsigned int nparts = PRENORM ? (unsigned int)__ldcg(&scratch->n_partials) : gridDim.x;
-      const double* vp = partials + (int64_t)s * nparts;
-      for (unsigned int b = threadIdx.x; b < nparts; b += 32) part += __ldcg(vp + b);
-      part = warp_sum(part);
-      if (threadIdx.x == 0) s_ss = part;
-    }
-    __syncthreads();
-    const double ss = PRENORM ? s_ss * (double)h.grad_scale * (double)h.grad_scale : s_ss;
-    __syncthreads();
-    const float g_norm = (float)sqrt(ss);
-    // optax.clip_by_global_norm: trigger = g_norm < max_norm
-    const float clip = (g_norm < seg.max_grad_norm) ? 1.0f : seg.max_grad_norm / g_norm;
-    const float gs = h.grad_scale * clip;
-    const int32_t c = cnt[s] + 1;
-    const float bc1 = 1.0f - powf(h.b1, (float)c);
-    const float bc2 = 1.0f - powf(h.b2, (float)c);
-    float lr = seg.init_lr;
-    if (h.decay) {
-      const int32_t k = sch[s] / h.steps_per_update;  // floor division, utils/training.py:25
-      lr = seg.init_lr * (1.0f - (float)k / (float)h.num_updates);
-    }
-    const float ob1 = 1.0f - h.b1, ob2 = 1.0f - h.b2;
+    const StxAdamSeg seg = s_seg[s];
+    const float gs = s_gs[s], bc1 = s_bc1[s], bc2 = s_bc2[s], lr = s_lr[s];
     float* p = P + seg.offset;
     float* mu = MU + seg.offset;
     float* nu = NU + seg.offset;
     const float* g = G + seg.offset;
     const int64_t n4 = seg.count / 4;
     for (int64_t i = gtid; i < n4; i += gthreads) {
-      float4 gv = reinterpret_cast<const float4*>(g)[i];
-      float4 m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
-      float4 pv = reinterpret_cast<float4*>(p)[i];
+      float4 gv, m, v, pv;
+      if (PRENORM && s < kPf && i == gtid) {
+        gv = pf_g[s < kPf ? s : 0], m = pf_m[s < kPf ? s : 0], v = pf_v[s < kPf ? s : 0], pv = pf_p[s < kPf ? s : 0];
+      } else {
+        gv = reinterpret_cast<const float4*>(g)[i];
+        m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
+        pv = reinterpret_cast<float4*>(p)[i];
+      }
       float ge[4] = {gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs};
       float me[4] = {m.x, m.y, m.z, m.w}, ve[4] = {v.x, v.y, v.z, v.w}, pe[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
@@ -217,10 +242,19 @@ __global__ void __launch_bounds__(kAdamThreads)
       mu[i] = me, nu[i] = ve, p[i] = pn;
       if (P16) P16[seg.offset + i] = __float2bfloat16_rn(pn);
     }
-    if (gtid == 0) {
-      counts[2 * s] = c;
-      counts[2 * s + 1] = sch[s] + 1;
-      if (gnorm_out) gnorm_out[s] = g_norm;
+  }
+  // The step counters are read by every block (above) and advanced by whichever block finishes LAST: no block can
+  // still need the old values then, with or without the grid barrier.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(finish, 1ull);
+    if (t % gridDim.x == gridDim.x - 1) {
+      for (int s = 0; s < nseg; ++s) {
+        counts[2 * s] += 1;
+        counts[2 * s + 1] += 1;
+        if (gnorm_out) gnorm_out[s] = s_gn[s];
+      }
     }
   }
 }

@@ -101,6 +101,51 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Actor head of one row: softmax statistics with ONE exponential per logit (e_j = exp(z_j - zmax), p_j = e_j / sum(e),
+// log p_j = (z_j - zmax) - log(sum(e))), the clipped-surrogate loss and d(loss)/d(logits) incl. the entropy bonus.
+// Fast intrinsics: this path carries bf16-level error anyway.  NA = compile-time bound on the action count.
+template <int NA>
+__device__ __forceinline__ void actor_head(const uint32_t (&r)[16], const float* s_b2, int A, int a, float logp_old, float adv,
+                                           float clip_eps, float ent_coef, float inv_m, float (&dz)[16], float& loss,
+                                           float& ent_out) {
+  float zs[NA], ex[NA], zmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+    zs[j] = __uint_as_float(r[j]) + s_b2[j];
+    if (j < A) zmax = fmaxf(zmax, zs[j]);
+  }
+  float se = 0.f;
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+    zs[j] -= zmax;
+    ex[j] = j < A ? __expf(zs[j]) : 0.f;
+    se += ex[j];
+  }
+  const float lse = __logf(se), inv_se = 1.0f / se;
+  float ent = 0.f, logp_a = 0.f;
+#pragma unroll
+  for (int j = 0; j < NA; ++j)
+    if (j < A) {
+      const float lp = zs[j] - lse;
+      ent -= ex[j] * inv_se * lp;
+      if (j == a) logp_a = lp;
+    }
+  const float ratio = __expf(logp_a - logp_old);
+  const float l1 = ratio * adv;
+  const float l2 = fminf(fmaxf(ratio, 1.0f - clip_eps), 1.0f + clip_eps) * adv;
+  const bool in_band = (ratio >= 1.0f - clip_eps) && (ratio <= 1.0f + clip_eps);
+  const float dlogp = ((l1 < l2) || in_band) ? -adv * ratio * inv_m : 0.f;
+  const float ce = ent_coef * inv_m;
+#pragma unroll
+  for (int j = 0; j < NA; ++j)
+    if (j < A) {
+      const float lp = zs[j] - lse, pr = ex[j] * inv_se;
+      dz[j] = dlogp * ((j == a ? 1.f : 0.f) - pr) + ce * pr * (lp + ent);
+    }
+  loss = -fminf(l1, l2);
+  ent_out = ent;
+}
+
 __global__ void __launch_bounds__(kFbThreads, 1)
     tc_ppo_fwd_bwd_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
                           const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
@@ -116,9 +161,11 @@ __global__ void __launch_bounds__(kFbThreads, 1)
   uint64_t* x_full = bars;       // [2]
   uint64_t* x_empty = bars + 2;  // [2]
   uint64_t* w_full = bars + 4;
-  uint64_t* mma_done = bars + 5;
-  uint64_t* epi_done = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* d_ready = bars + 5;      // [4] MMA -> epilogue: column part p of the current GEMM is complete
+  uint64_t* chunk_done = bars + 9;   // [4] epilogue -> MMA: part p consumed (and its slice of the next A operand written)
+  uint64_t* head_ready = bars + 13;  // G2 complete
+  uint64_t* head_done = bars + 14;   // dz tile in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int which = (int)blockIdx.x < p.n_cta[0] ? 0 : 1;
@@ -136,8 +183,12 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(w_full, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(epi_done, 8);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&d_ready[i], 1);
+      mbar_init(&chunk_done[i], 8);  // 4 lane quarters x 2 column halves
+    }
+    mbar_init(head_ready, 1);
+    mbar_init(head_done, 4);
     fence_barrier_init();
     tma_prefetch_desc(tmW0);
     tma_prefetch_desc(tmW1);
@@ -210,76 +261,98 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     }
   } else if (warp == kFbMmaWarp) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_fwd = idesc_bf16(128, 256, 0, 1);   // B = W (in,out) image as MN-major
+    // Every 256-wide GEMM is issued as four N=64 column parts.  Part p of the NEXT GEMM only needs (a) D part p
+    // consumed by the running epilogue and (b) the K-chunks of its A operand written, both announced per part
+    // through chunk_done[]; so the tensor pipe trails the epilogue part by part instead of waiting for all of it.
+    constexpr uint32_t idesc_fwd = idesc_bf16(128, 64, 0, 1);    // B = W (in,out) image as MN-major
     constexpr uint32_t idesc_head = idesc_bf16(128, 16, 0, 1);
-    constexpr uint32_t idesc_bwd = idesc_bf16(128, 256, 0, 0);   // B = same images read as K-major
+    constexpr uint32_t idesc_bwd = idesc_bf16(128, 64, 0, 0);    // B = same images read as K-major
+    constexpr uint32_t idesc_bwd_full = idesc_bf16(128, 256, 0, 0);
     const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
     mbar_wait(w_full, 0, 2);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
-      const int g0 = 5 * it;
       STX_STAMP(0);
       mbar_wait(&x_full[s], (it >> 1) & 1, 3);
-      if (g0 > 0) mbar_wait(epi_done, (g0 - 1) & 1, 4);
-      tc_fence_after();
+      const uint32_t xa = sbase + kOffX + s * 16384;
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {  // G0: D = X * W0, trailing E4 of the previous tile
+        if (it > 0) mbar_wait(&chunk_done[pt], 1, 4);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_d + pt * 64, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
+                   smem_desc(sbase + kOffW0 + pt * 8192 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+          mma_commit(&d_ready[pt]);
+          if (pt == 3) mma_commit(&x_empty[s]);
+        }
+        __syncwarp();
+      }
       STX_STAMP(1);
-      if (elect_one()) {  // G0: D = X * W0
-        const uint32_t xa = sbase + kOffX + s * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_ss(tmem_d, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
-                 smem_desc(sbase + kOffW0 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
-        mma_commit(&x_empty[s]);
-        mma_commit(mma_done);
+      for (int j = 0; j < 4; ++j) {  // G1: D = h1 * W1, trailing E0
+        mbar_wait(&chunk_done[j], 0, 5);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll
+            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
+              mma_ts(tmem_d + pt * 64, tmem_a1 + k * 8,
+                     smem_desc(sbase + kOffW1 + pt * 32768 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+            if (j == 3) mma_commit(&d_ready[pt]);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      STX_STAMP(2);
-      mbar_wait(epi_done, g0 & 1, 5);
-      tc_fence_after();
       STX_STAMP(3);
-      if (elect_one()) {  // G1: D = h1 * W1
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          mma_ts(tmem_d, tmem_a1 + k * 8, smem_desc(sbase + kOffW1 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
-        mma_commit(mma_done);
+      for (int j = 0; j < 4; ++j) {  // G2: D[:, :16] = h2 * W2, trailing E1 (columns 0..15 are free after its first part)
+        mbar_wait(&chunk_done[j], 1, 6);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 4 * j; k < 4 * j + 4; ++k)
+            mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_head, k > 0);
+          if (j == 3) mma_commit(head_ready);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      STX_STAMP(4);
-      mbar_wait(epi_done, (g0 + 1) & 1, 6);
-      tc_fence_after();
       STX_STAMP(5);
-      if (elect_one()) {  // G2: D[:, :16] = h2 * W2
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_head, k > 0);
-        mma_commit(mma_done);
-      }
-      __syncwarp();
-      STX_STAMP(6);
-      mbar_wait(epi_done, (g0 + 2) & 1, 7);
+      mbar_wait(head_done, it & 1, 7);
       tc_fence_after();
-      STX_STAMP(7);
       if (elect_one()) {  // G3: D = dz (smem, K-major core matrices) * W2^T (same W2 image, K-major)
         mma_ss(tmem_d, smem_desc(sbase + kOffDz, 128, 256, SWIZZLE_NONE), smem_desc(sbase + kOffW2, 128, 256, SWIZZLE_NONE),
-               idesc_bwd, 0);
-        mma_commit(mma_done);
-      }
-      __syncwarp();
-      STX_STAMP(8);
-      mbar_wait(epi_done, (g0 + 3) & 1, 8);
-      tc_fence_after();
-      STX_STAMP(9);
-      if (elect_one()) {  // G4: D = dh2 * W1^T  (W1 image as K-major SW128: 4 K-blocks of 64)
+               idesc_bwd_full, 0);
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW1 + (k >> 2) * 32768 + (k & 3) * 32, 16, 1024, SWIZZLE_128B),
-                 idesc_bwd, k > 0);
-        mma_commit(mma_done);
+        for (int pt = 0; pt < 4; ++pt) mma_commit(&d_ready[pt]);
       }
       __syncwarp();
+      STX_STAMP(7);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // G4: D = dh2 * W1^T, trailing E3  (W1 image as K-major SW128: 4 K-blocks of 64)
+        mbar_wait(&chunk_done[j], 0, 8);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll
+            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
+              mma_ts(tmem_d + pt * 64, tmem_a2 + k * 8,
+                     smem_desc(sbase + kOffW1 + (k >> 2) * 32768 + pt * 8192 + (k & 3) * 32, 16, 1024, SWIZZLE_128B), idesc_bwd,
+                     k > 0);
+            if (j == 3) mma_commit(&d_ready[pt]);
+          }
+        }
+        __syncwarp();
+      }
+      STX_STAMP(9);
     }
   } else {
     // ===================== epilogue warps 5..12: lane quarter q = warp % 4, column half `half` =====================
+    // Time step cc of an epilogue handles the two 32-column chunks of part cc (chunk 2cc by the half-0 warps,
+    // 2cc+1 by the half-1 warps), so parts complete in order and are handed to the MMA warp one by one.
     const int q = warp & 3, half = (warp - 5) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
@@ -296,7 +369,6 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
-      const int g0 = 5 * it;
       // per-row loss inputs: issued now, consumed in E2 (their latency hides behind E0/E1)
       int pf_a = 0;
       float pf_0 = 0.f, pf_1 = 0.f;
@@ -313,15 +385,15 @@ __global__ void __launch_bounds__(kFbThreads, 1)
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         if (warp == 5) STX_STAMP(16 + 2 * layer);
-        mbar_wait(mma_done, (g0 + layer) & 1, 10 + layer);
-        tc_fence_after();
-        if (warp == 5) STX_STAMP(17 + 2 * layer);
         const float* bias = layer == 0 ? s_b0 : s_b1;
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
         __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
-          const int c = half * 4 + cc;
+          const int c = cc * 2 + half;
+          mbar_wait(&d_ready[cc], layer, 10 + layer);  // G0 / G1 are the 1st / 2nd completion of d_ready per tile
+          tc_fence_after();
+          if (warp == 5 && cc == 0) STX_STAMP(17 + 2 * layer);
           uint32_t r[32], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -332,69 +404,33 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             pk[j] = pack_bf16(v0, v1);
           }
           tmem_st16(ta + c * 16, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[cc]);  // D part cc consumed, K-chunks of part cc written
 #pragma unroll
           for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
             *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
       }
       // ---------------- E2: head + loss + d(head) ----------------
       if (warp == 5) STX_STAMP(20);
-      mbar_wait(mma_done, (g0 + 2) & 1, 12);
-      tc_fence_after();
-      if (warp == 5) STX_STAMP(21);
       if (half == 0) {
+        mbar_wait(head_ready, it & 1, 12);
+        tc_fence_after();
+        if (warp == 5) STX_STAMP(21);
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
-        if (warp == 5) STX_STAMP(40);
         float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dz[j] = 0.f;
         if (net.is_actor) {
-          const int A = net.A;
-          // softmax statistics with ONE exponential per logit: e_j = exp(z_j - zmax), p_j = e_j / sum(e),
-          // log p_j = (z_j - zmax) - log(sum(e)).  Fast intrinsics: this path carries bf16-level error anyway.
-          float zs[16], ex[16], zmax = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            zs[j] = __uint_as_float(r[j]) + s_b2[j];
-            if (j < A) zmax = fmaxf(zmax, zs[j]);
-          }
-          float se = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            zs[j] -= zmax;
-            ex[j] = j < A ? __expf(zs[j]) : 0.f;
-            se += ex[j];
-          }
-          const float lse = __logf(se), inv_se = 1.0f / se;
-          const int a = pf_a;
           const float adv = (pf_1 - adv_mean) * adv_rstd;
-          float ent = 0.f, logp_a = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < A) {
-              const float lp = zs[j] - lse;
-              ent -= ex[j] * inv_se * lp;
-              if (j == a) logp_a = lp;
-            }
-          const float ratio = __expf(logp_a - pf_0);
-          const float l1 = ratio * adv;
-          const float l2 = fminf(fmaxf(ratio, 1.0f - p.clip_eps), 1.0f + p.clip_eps) * adv;
-          const bool in_band = (ratio >= 1.0f - p.clip_eps) && (ratio <= 1.0f + p.clip_eps);
-          const float dlogp = ((l1 < l2) || in_band) ? -adv * ratio * inv_m : 0.f;
-          const float ce = p.ent_coef * inv_m;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < A) {
-              const float lp = zs[j] - lse, pr = ex[j] * inv_se;
-              dz[j] = dlogp * ((j == a ? 1.f : 0.f) - pr) + ce * pr * (lp + ent);
-            }
-          m_acc[0] += -fminf(l1, l2), m_acc[1] += ent, m_acc[3] += adv;
+          float loss, ent;
+          if (net.A <= 8) actor_head<8>(r, s_b2, net.A, pf_a, pf_0, adv, p.clip_eps, p.ent_coef, inv_m, dz, loss, ent);
+          else actor_head<16>(r, s_b2, net.A, pf_a, pf_0, adv, p.clip_eps, p.ent_coef, inv_m, dz, loss, ent);
+          m_acc[0] += loss, m_acc[1] += ent, m_acc[3] += adv;
         } else {
           const float v = __uint_as_float(r[0]) + s_b2[0], vo = pf_0, tg = pf_1;
           const float diff = v - vo;
@@ -406,9 +442,24 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           m_acc[2] += 0.5f * fmaxf(q1, q2), m_acc[4] += v, m_acc[5] += tg;
         }
         if (warp == 5) STX_STAMP(41);
-        // bias gradient of the head: column sums over the 32 rows of this warp (16 columns)
+        // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(dz[2 * j], dz[2 * j + 1]);
+        const int mr = q * 32 + lane;
+        uint8_t* dzs = smem + kOffDz + (mr >> 3) * 256 + (mr & 7) * 16;
+        *reinterpret_cast<uint4*>(dzs) = make_uint4(pk[0], pk[1], pk[2], pk[3]);        // k = 0..7
+        *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
+        fence_async_proxy();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(head_done);
+        if (warp == 5) STX_STAMP(44);
+        *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        // bias gradient of the head (off the critical path: G3 is already running): column sums over the 32 rows
+        // of this warp; fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
         {
-          // 16 columns: fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
           float t[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) t[j] = dz[j] + __shfl_xor_sync(0xffffffffu, dz[j], 16);
@@ -424,37 +475,19 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           }
           if (lane < 16) s_db[q * 528 + 512 + lane] += t[0];  // lanes 0..15 hold columns 0..15
         }
-        if (warp == 5) STX_STAMP(42);
-        // dz -> bf16: smem A operand (core-matrix K-major) + global (padded row of 64)
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(dz[2 * j], dz[2 * j + 1]);
-        const int mr = q * 32 + lane;
-        uint8_t* dzs = smem + kOffDz + (mr >> 3) * 256 + (mr & 7) * 16;
-        *reinterpret_cast<uint4*>(dzs) = make_uint4(pk[0], pk[1], pk[2], pk[3]);        // k = 0..7
-        *reinterpret_cast<uint4*>(dzs + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);  // k = 8..15
-        *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (warp == 5) STX_STAMP(43);
-        fence_async_proxy();
-        if (warp == 5) STX_STAMP(44);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(epi_done);
       // ---------------- E3 / E4: dh2 = D * (h2 > 0) ; dh1 = D * (h1 > 0) ----------------
 #pragma unroll 1
       for (int layer = 1; layer >= 0; --layer) {
         if (warp == 5) STX_STAMP(22 + 2 * (1 - layer));
-        mbar_wait(mma_done, (g0 + 3 + (1 - layer)) & 1, 13 + layer);
-        tc_fence_after();
-        if (warp == 5) STX_STAMP(23 + 2 * (1 - layer));
         const uint32_t ta = layer == 1 ? tmem_a2 : tmem_a1;  // packed h of this layer (mask source)
         __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
-          const int c = half * 4 + cc;
+          const int c = cc * 2 + half;
+          mbar_wait(&d_ready[cc], 1 - layer, 13 + layer);  // G3 / G4 are the 3rd / 4th completion per tile
+          tc_fence_after();
           uint32_t r[32], hm[16], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld16(ta + c * 16, hm);
@@ -468,17 +501,19 @@ __global__ void __launch_bounds__(kFbThreads, 1)
             dv[2 * j + 1] = p1 ? __uint_as_float(r[2 * j + 1]) : 0.f;
             pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
           }
-          if (layer == 1) tmem_st16(ta + c * 16, pk);  // dh2 replaces h2 as the A operand of G4
+          if (layer == 1) {  // dh2 replaces h2 as the A operand of G4
+            tmem_st16(ta + c * 16, pk);
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[cc]);  // E3: -> G4 part cc ; E4: D part cc free for the next tile's G0
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           const float cs = warp_colsum32(dv, lane);
           dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
         }
-        if (layer == 1) tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
         if (warp == 5) STX_STAMP(26 + (1 - layer));
       }
     }
@@ -607,13 +642,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
   } else {
     const int q = warp & 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* out = job.part + (int64_t)cta * 256 * job.N;
+    // partial layout [N/4][256 rows][4]: the 32 lanes of a warp (= 32 consecutive rows) write 512 contiguous bytes
+    float4* out = reinterpret_cast<float4*>(job.part + (int64_t)cta * 256 * job.N);
     if (my_chunks > 0) {
       mbar_wait(acc_done, 0, 22);
       tc_fence_after();
     }
     for (int h = 0; h < 2; ++h) {
-      float* orow = out + (int64_t)(h * 128 + q * 32 + lane) * job.N;
+      const int m = h * 128 + q * 32 + lane;
       for (int c = 0; c < job.N / 16; ++c) {
         uint32_t r[16];
         if (my_chunks > 0) {
@@ -623,11 +659,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] = 0u;
         }
-        float4* dst = reinterpret_cast<float4*>(orow + c * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                               __uint_as_float(r[4 * i + 3]));
+          out[(int64_t)(c * 4 + i) * 256 + m] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
       }
     }
   }
@@ -650,7 +685,7 @@ struct RedSeg {
   int dst_ld;
   int64_t dst_off;
   int net;              // optimiser segment (0 actor, 1 critic) for the sum-of-squares side output
-  int vec;              // 1: process 4 consecutive columns per item with 128-bit accesses
+  int cg4;              // 1: source is a K3b partial in [cols/4][256 rows][4] order (items enumerate it linearly)
   int items;            // rows*cols/4 (vec) or rows*cols
 };
 struct RedParams {
@@ -681,8 +716,16 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
     while (i >= p.seg[s].items) i -= p.seg[s].items, ++s;
     const RedSeg& g = p.seg[s];
     {
-      const int r = i / g.cols, c = i % g.cols;
-      const float* src = g.part + (int64_t)r * g.src_ld + c;
+      int r, c;
+      const float* src;
+      if (g.cg4) {  // linear walk over the partial: coalesced reads; (r, c) = (row, column) of the K3b output
+        r = (i & 1023) >> 2, c = ((i >> 10) << 2) | (i & 3);
+        if (c >= g.cols) continue;
+        src = g.part + i;
+      } else {
+        r = i / g.cols, c = i % g.cols;
+        src = g.part + (int64_t)r * g.src_ld + c;
+      }
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // many short independent chains: this kernel is latency-bound
       int k = 0;
       for (; k + 4 <= g.n_part; k += 4) {
@@ -846,12 +889,12 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   RedParams rp{};
   int sidx = 0;
   auto add_seg = [&](const float* part, int64_t stride, int n_part, int rows, int cols, int src_ld, int transpose, int dst_ld,
-                     int64_t dst_off, int net_id) {
+                     int64_t dst_off, int net_id, int cg4) {
     RedSeg g{};
     g.part = part, g.part_stride = stride, g.n_part = n_part, g.rows = rows, g.cols = cols, g.src_ld = src_ld;
     g.transpose = transpose, g.dst_ld = dst_ld, g.dst_off = dst_off, g.net = net_id;
-    g.vec = 0;  // scalar items: 4x the threads of a float4 version and measurably faster (latency-bound)
-    g.items = g.vec ? rows * cols / 4 : rows * cols;
+    g.cg4 = cg4;
+    g.items = cg4 ? ((cols + 3) / 4) * 1024 : rows * cols;  // scalar items (4x the threads of a float4 version: measurably faster)
     rp.total_items += g.items;
     rp.seg[sidx++] = g;
   };
@@ -859,12 +902,12 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     const int A = nets[n]->sizes[3];
     const int64_t o_w0 = noff[n], o_b0 = o_w0 + (int64_t)D * kH, o_w1 = o_b0 + kH, o_b1 = o_w1 + (int64_t)kH * kH, o_w2 = o_b1 + kH,
                   o_b2 = o_w2 + (int64_t)kH * A;
-    add_seg(ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, kH, o_w1, n);              // dW1[in][out]
-    add_seg(ws.part_w0[n], 256 * 64, kDwCtaW0, kH, D, 64, 1, kH, o_w0, n);             // part[j][d] -> W0[d][j]
-    add_seg(ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, A, o_w2, n);              // dW2[j][a]
-    add_seg(ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b0, n);
-    add_seg(ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b1, n);
-    add_seg(ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, A, o_b2, n);
+    add_seg(ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, kH, o_w1, n, 1);           // dW1[in][out]
+    add_seg(ws.part_w0[n], 256 * 64, kDwCtaW0, kH, D, 64, 1, kH, o_w0, n, 1);          // part(j, d) -> W0[d][j]
+    add_seg(ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, A, o_w2, n, 1);           // dW2[j][a]
+    add_seg(ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b0, n, 0);
+    add_seg(ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b1, n, 0);
+    add_seg(ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, A, o_b2, n, 0);
   }
   rp.n_seg = sidx;
   rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
