@@ -31,6 +31,10 @@ names = {0: "mma: tile start", 1: "mma: G0 issued (all parts)", 3: "mma: G1 issu
          21: "epi: head ready", 41: "E2: loss math done", 44: "E2: dz in smem, head_done arrived", 22: "epi: E3 start", 24: "epi: E4 start",
          26: "epi: E3 finished", 27: "epi: E4 finished", 48: "prod: loads issued (tile 1)", 49: "prod: x_empty ok", 50: "prod: smem+xg stores issued",
          51: "prod: fence done"}
+names.update({56: "kernel entry", 57: "setup done (barriers, TMEM, W2, biases)", 58: "mma: W0/W1 landed", 59: "mma: first X tile landed",
+              61: "epi: all tiles done", 62: "kernel exit (thread 0)"})
+for t in range(4):
+    names.update({32 + 4 * t: f"tile {t}: E0 start", 33 + 4 * t: f"tile {t}: E2 start", 34 + 4 * t: f"tile {t}: E3 end", 35 + 4 * t: f"tile {t}: E4 end"})
 for k in sorted(names, key=lambda k: c[k]):
     if c[k] > 0:
         print(f"{c[k] - base:8d} cyc  {names[k]}")

@@ -33,14 +33,16 @@ int make_map_tiled(CUtensorMap* m, const void* base, uint64_t tiles, uint32_t co
 
 // optional timeline instrumentation (scripts/profile_k3_timeline.py): clock64 stamps of CTA 0, tile 1
 __device__ long long* g_clock_buf = nullptr;
-#define STX_STAMP(slot)                                                              \
-  do {                                                                               \
-    if (g_clock_buf != nullptr && blockIdx.x == 0 && it == 1 && lane == 0) g_clock_buf[slot] = clock64(); \
+#define STX_STAMP_AT(slot, cond)                                   \
+  do {                                                             \
+    if (clk_buf != nullptr && (cond)) clk_buf[slot] = clock64();   \
   } while (0)
+#define STX_STAMP(slot) STX_STAMP_AT(slot, it == 1 && lane == 0)
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;
-constexpr int kFbThreads = 416;  // warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5..12 epilogue
+// warps 0..3 gather producers (one row per thread), warp 4 MMA, warps 5.. epilogue (8 or 16 of them)
+constexpr int fb_threads(int nepi) { return 32 * (5 + nepi); }
 constexpr int kFbMmaWarp = 4;
 
 // ---- K3a shared-memory map ------------------------------------------------------------------------
@@ -146,13 +148,17 @@ __device__ __forceinline__ void actor_head(const uint32_t (&r)[16], const float*
   ent_out = ent;
 }
 
-__global__ void __launch_bounds__(kFbThreads, 1)
+template <int NEPI>
+__global__ void __launch_bounds__(fb_threads(NEPI), 1)
     tc_ppo_fwd_bwd_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
                           const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
                           const FbParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET (not through an integer cast) so that the compiler keeps the shared address space: LDS/STS, not generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
+  long long* const clk_buf = blockIdx.x == 0 ? g_clock_buf : nullptr;  // one load; the stamps themselves stay cheap
+  STX_STAMP_AT(56, threadIdx.x == 0);
   float* s_b0 = reinterpret_cast<float*>(smem + kOffBias);
   float* s_b1 = s_b0 + 256;
   float* s_b2 = s_b1 + 256;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
   {
     // one thread per W2 row: all of its (<=16) loads are independent and in flight together
     uint8_t* w2s = smem + kOffW2;
-    for (int j = threadIdx.x; j < kH; j += kFbThreads) {
+    for (int j = threadIdx.x; j < kH; j += fb_threads(NEPI)) {
       uint32_t pk[8];
       if (net.A == 8 && (reinterpret_cast<uintptr_t>(net.w2) & 15) == 0) {
         const uint4 v = *reinterpret_cast<const uint4*>(net.w2 + j * 8);
@@ -213,15 +219,16 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    for (int i = threadIdx.x; i < 256; i += kFbThreads) s_b0[i] = net.b0[i], s_b1[i] = net.b1[i];
+    for (int i = threadIdx.x; i < 256; i += fb_threads(NEPI)) s_b0[i] = net.b0[i], s_b1[i] = net.b1[i];
     if (threadIdx.x < 16) s_b2[threadIdx.x] = threadIdx.x < net.A ? net.b2[threadIdx.x] : 0.f;
-    for (int i = threadIdx.x; i < 4 * 528; i += kFbThreads) s_db[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 528; i += fb_threads(NEPI)) s_db[i] = 0.f;
     fence_async_proxy();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  STX_STAMP_AT(57, threadIdx.x == 0);
 
   float m_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actor_loss, entropy, value_loss, adv, pred value, target
 
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     constexpr uint32_t idesc_bwd_full = idesc_bf16(128, 256, 0, 0);
     const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
     mbar_wait(w_full, 0, 2);
+    STX_STAMP_AT(58, lane == 0);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       STX_STAMP(0);
@@ -350,10 +358,12 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       STX_STAMP(9);
     }
   } else {
-    // ===================== epilogue warps 5..12: lane quarter q = warp % 4, column half `half` =====================
-    // Time step cc of an epilogue handles the two 32-column chunks of part cc (chunk 2cc by the half-0 warps,
-    // 2cc+1 by the half-1 warps), so parts complete in order and are handed to the MMA warp one by one.
-    const int q = warp & 3, half = (warp - 5) >> 2;
+    // ===================== epilogue warps 5..: lane quarter q = warp % 4, column position `sub` =====================
+    // Time step cc of an epilogue handles the 32-column chunks cc*kSub + sub (kSub = NEPI/4 warps per lane quarter), so
+    // the 64-column parts complete in order and are handed to the MMA warp one by one (NEPI=8: one part per step,
+    // NEPI=16: two parts per step).
+    constexpr int kSub = NEPI / 4, kSteps = 8 / kSub;
+    const int q = warp & 3, sub = (warp - 5) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
     const float inv_m = 1.0f / (float)p.mb;
@@ -361,27 +371,23 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     if (p.adv_stats) adv_mean = p.adv_stats[0], adv_rstd = p.adv_stats[1];
     // source row of this thread's row in the NEXT tile: loaded one tile ahead so that the dependent per-row
     // loads below never wait on the index (two chained DRAM latencies would otherwise open every tile)
-    int64_t src_next = 0;
-    if (half == 0 && my_tiles > 0) {
-      const int64_t r0 = (int64_t)cta_in_net * kTileM + q * 32 + lane;
-      src_next = p.idx ? (int64_t)p.idx[r0] : p.row0 + r0;
-    }
+    // (kept RAW: a conversion right behind the load would stall this in-order warp for the full memory latency)
+    int32_t idx_next = 0;
+    if (sub == 0 && my_tiles > 0 && p.idx) idx_next = p.idx[(int64_t)cta_in_net * kTileM + q * 32 + lane];
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
       // per-row loss inputs: issued now, consumed in E2 (their latency hides behind E0/E1)
       int pf_a = 0;
       float pf_0 = 0.f, pf_1 = 0.f;
-      if (half == 0) {
-        const int64_t src = src_next;
+      if (sub == 0) {
+        const int64_t src = p.idx ? (int64_t)idx_next : p.row0 + mrow;
         if (net.is_actor) pf_a = p.action[src], pf_0 = p.logp_old[src], pf_1 = p.adv[src];
         else pf_0 = p.v_old[src], pf_1 = p.tgt[src];
-        if (it + 1 < my_tiles) {
-          const int64_t rn = mrow + (int64_t)ncta * kTileM;
-          src_next = p.idx ? (int64_t)p.idx[rn] : p.row0 + rn;
-        }
+        if (it + 1 < my_tiles && p.idx) idx_next = p.idx[mrow + (int64_t)ncta * kTileM];
       }
       // ---------------- E0 / E1: hidden layers ----------------
+      STX_STAMP_AT(32 + 4 * it, warp == 5 && lane == 0 && it < 4);  // 32, 36, 40, 44: E0 start of tile it
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         if (warp == 5) STX_STAMP(16 + 2 * layer);
@@ -389,9 +395,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
         __nv_bfloat16* hout = layer == 0 ? net.h1 : net.h2;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = cc * 2 + half;
-          mbar_wait(&d_ready[cc], layer, 10 + layer);  // G0 / G1 are the 1st / 2nd completion of d_ready per tile
+        for (int cc = 0; cc < kSteps; ++cc) {
+          const int c = cc * kSub + sub, part = c >> 1;
+          mbar_wait(&d_ready[part], layer, 10 + layer);  // G0 / G1 are the 1st / 2nd completion of d_ready per tile
           tc_fence_after();
           if (warp == 5 && cc == 0) STX_STAMP(17 + 2 * layer);
           uint32_t r[32], pk[16];
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&chunk_done[cc]);  // D part cc consumed, K-chunks of part cc written
+          if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
 #pragma unroll
           for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
             *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -415,7 +421,8 @@ __global__ void __launch_bounds__(kFbThreads, 1)
       }
       // ---------------- E2: head + loss + d(head) ----------------
       if (warp == 5) STX_STAMP(20);
-      if (half == 0) {
+      STX_STAMP_AT(32 + 4 * it + 1, warp == 5 && lane == 0 && it < 4);  // E2 start of tile it
+      if (sub == 0) {
         mbar_wait(head_ready, it & 1, 12);
         tc_fence_after();
         if (warp == 5) STX_STAMP(21);
@@ -484,9 +491,9 @@ __global__ void __launch_bounds__(kFbThreads, 1)
         __nv_bfloat16* dout = layer == 1 ? net.dh2 : net.dh1;
         float* dbacc = s_db + q * 528 + (layer == 1 ? 256 : 0);
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = cc * 2 + half;
-          mbar_wait(&d_ready[cc], 1 - layer, 13 + layer);  // G3 / G4 are the 3rd / 4th completion per tile
+        for (int cc = 0; cc < kSteps; ++cc) {
+          const int c = cc * kSub + sub, part = c >> 1;
+          mbar_wait(&d_ready[part], 1 - layer, 13 + layer);  // G3 / G4 are the 3rd / 4th completion per tile
           tc_fence_after();
           uint32_t r[32], hm[16], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
@@ -507,7 +514,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&chunk_done[cc]);  // E3: -> G4 part cc ; E4: D part cc free for the next tile's G0
+          if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -515,16 +522,18 @@ __global__ void __launch_bounds__(kFbThreads, 1)
           dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
         }
         if (warp == 5) STX_STAMP(26 + (1 - layer));
+        STX_STAMP_AT(32 + 4 * it + 2 + (1 - layer), warp == 5 && lane == 0 && it < 4);  // E3 / E4 end of tile it
       }
     }
+    STX_STAMP_AT(61, warp == 5 && lane == 0);
   }
   // ---- teardown: bias-gradient and metric partials of this CTA ----
   tc_fence_before();
   __syncthreads();
-  for (int i = threadIdx.x; i < 528; i += kFbThreads)
+  for (int i = threadIdx.x; i < 528; i += fb_threads(NEPI))
     net.db_part[(int64_t)cta_in_net * 528 + i] = (s_db[i] + s_db[528 + i]) + (s_db[2 * 528 + i] + s_db[3 * 528 + i]);
   {
-    __shared__ float s_mw[kFbThreads / 32][6];
+    __shared__ float s_mw[fb_threads(NEPI) / 32][6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const float w = warp_sum(m_acc[k]);
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     if (threadIdx.x < 8) {
       float acc = 0.f;
       if (threadIdx.x < 6)
-        for (int w = 0; w < kFbThreads / 32; ++w) acc += s_mw[w][threadIdx.x];
+        for (int w = 0; w < fb_threads(NEPI) / 32; ++w) acc += s_mw[w][threadIdx.x];
       p.metric_part[(int64_t)blockIdx.x * 8 + threadIdx.x] = acc;
     }
   }
@@ -542,6 +551,7 @@ __global__ void __launch_bounds__(kFbThreads, 1)
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  STX_STAMP_AT(62, threadIdx.x == 0);
 }
 
 // =============================== K3b: dW = A^T * B ===============================================
@@ -851,11 +861,12 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
 
   static bool attr_set = false;
   if (!attr_set) {
-    STX_CUDA_OK(cudaFuncSetAttribute(tc_ppo_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbSmemBytes));
+    STX_CUDA_OK(cudaFuncSetAttribute(tc_ppo_fwd_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbSmemBytes));
     STX_CUDA_OK(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
     attr_set = true;
   }
-  tc_ppo_fwd_bwd_kernel<<<2 * kCtaPerNet, kFbThreads, kFbSmemBytes, st>>>(tmW0[0], tmW1[0], tmW0[1], tmW1[1], fp);
+  // 8 epilogue warps: 16 (two parts per step, 80 registers) measured 5 % slower (profiles/README.md)
+  tc_ppo_fwd_bwd_kernel<8><<<2 * kCtaPerNet, fb_threads(8), kFbSmemBytes, st>>>(tmW0[0], tmW1[0], tmW0[1], tmW1[1], fp);
   STX_LAUNCH_OK();
 
   // ---- K3b ----
