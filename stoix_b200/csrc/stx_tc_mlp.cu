@@ -28,7 +28,6 @@ constexpr int kTileM = 128;
 constexpr int kH = 256;
 constexpr int kXStages = 2;
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: hides the tcgen05.ld / pack latencies
-constexpr int kChunksPerWarp = 8 / (kEpiWarps / 4);
 constexpr int kThreads = 32 * (2 + kEpiWarps);  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 // shared-memory map (bytes from a 1024-aligned base)
@@ -55,7 +54,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
                       const __grid_constant__ CUtensorMap tmW1, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET (not through an integer cast) so that the compiler keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   float* s_b0 = reinterpret_cast<float*>(smem + kOffBias);
   float* s_b1 = s_b0 + 256;
@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* x_full = bars;             // [kXStages]
   uint64_t* x_empty = bars + 2;        // [kXStages]
   uint64_t* w_full = bars + 4;
-  uint64_t* mma_done = bars + 5;
-  uint64_t* epi_done = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* d_ready = bars + 5;      // [4] MMA -> epilogue: 64-column part p of the current layer's accumulator is complete
+  uint64_t* chunk_done = bars + 9;   // [4] epilogue -> MMA: part p consumed and its slice of the next A operand written
+  uint64_t* head_ready = bars + 13;  // head GEMM complete
+  uint64_t* head_done = bars + 14;   // head read out of tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -76,8 +78,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(w_full, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(epi_done, kEpiWarps);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&d_ready[i], 1);
+      mbar_init(&chunk_done[i], 8);  // 4 lane quarters x 2 chunks of 32 columns
+    }
+    mbar_init(head_ready, 1);
+    mbar_init(head_done, 4);
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW0);
@@ -131,63 +137,80 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_n256 = idesc_bf16(128, 256, 0, 1);
+    // Every 256-wide GEMM is issued as four N=64 column parts; part p of the NEXT layer only needs D part p consumed
+    // and the K-chunks of its A operand written (chunk_done[]), so the tensor pipe trails the epilogue part by part
+    // (same scheme as K3a in stx_tc_ppo.cu).  h1 and h2 live in separate TMEM regions for that reason.
+    constexpr uint32_t idesc_n64 = idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t idesc_n16 = idesc_bf16(128, 16, 0, 1);
-    const uint32_t tmem_d = tmem, tmem_a = tmem + 256;
+    const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
     mbar_wait(w_full, 0, 2);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % kXStages;
-      const int g0 = 3 * it;
       mbar_wait(&x_full[s], (it / kXStages) & 1, 3);
-      if (g0 > 0) mbar_wait(epi_done, (g0 - 1) & 1, 4);  // previous tile's head epilogue has drained D
+      if (it > 0) mbar_wait(head_done, (it - 1) & 1, 4);  // the previous tile's head has left D columns 0..15
       tc_fence_after();
       if (elect_one()) {
         const uint32_t xa = sbase + kOffX + s * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // layer 0: D0 = X (K-major SW128) * W0 (MN-major SW128), K = 64
-          mma_ss(tmem_d, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
-                 smem_desc(sbase + kOffW0 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_n256, k > 0);
+        for (int pt = 0; pt < 4; ++pt) {  // layer 0: D0 = X (K-major SW128) * W0 (MN-major SW128), K = 64
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_d + pt * 64, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
+                   smem_desc(sbase + kOffW0 + pt * 8192 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_n64, k > 0);
+          mma_commit(&d_ready[pt]);
+        }
         mma_commit(&x_empty[s]);
-        mma_commit(mma_done);
       }
       __syncwarp();
-      mbar_wait(epi_done, g0 & 1, 5);  // A1 = relu(D0 + b0) is in TMEM
-      tc_fence_after();
-      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)  // layer 1: D1 = A1 (TMEM) * W1, K = 256
-          mma_ts(tmem_d, tmem_a + k * 8, smem_desc(sbase + kOffW1 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_n256, k > 0);
-        mma_commit(mma_done);
-      }
-      __syncwarp();
-      mbar_wait(epi_done, (g0 + 1) & 1, 6);  // A2 ready
-      tc_fence_after();
-      if (elect_one()) {
+      for (int j = 0; j < 4; ++j) {  // layer 1: D1 = A1 (TMEM) * W1, K = 256, trailing E0
+        mbar_wait(&chunk_done[j], 0, 5);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)  // head: D2 = A2 (TMEM) * W2 (un-swizzled core matrices), N = 16
-          mma_ts(tmem_d, tmem_a + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_n16, k > 0);
-        mma_commit(mma_done);
+          for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll
+            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
+              mma_ts(tmem_d + pt * 64, tmem_a1 + k * 8, smem_desc(sbase + kOffW1 + pt * 32768 + k * 2048, 32768, 1024, SWIZZLE_128B),
+                     idesc_n64, k > 0);
+            if (j == 3) mma_commit(&d_ready[pt]);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // head: D2 = A2 (TMEM) * W2 (un-swizzled core matrices), N = 16, trailing E1
+        mbar_wait(&chunk_done[j], 1, 6);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 4 * j; k < 4 * j + 4; ++k)
+            mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_n16, k > 0);
+          if (j == 3) mma_commit(head_ready);
+        }
+        __syncwarp();
+      }
     }
   } else {
-    // ===================== epilogue warps: lane quarter q = warp % 4, `sub` picks the column chunks =============
+    // ===================== epilogue warps: lane quarter q = warp % 4, `sub` picks the column chunk of a step =============
+    // step cc handles the 32-column chunks cc*kSub + sub (kSub warps per lane quarter): two 64-column parts per step
+    constexpr int kSub = kEpiWarps / 4, kSteps = 8 / kSub;
     const int q = warp & 3, sub = (warp - 2) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t tmem_d = tmem + lane_addr, tmem_a = tmem + lane_addr + 256;
+    const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int64_t row = (int64_t)tile * kTileM + q * 32 + lane;
-      const int g0 = 3 * it;
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(mma_done, (g0 + layer) & 1, 7 + layer);
-        tc_fence_after();
         const float* bias = layer == 0 ? s_b0 : s_b1;
         float* dbg = layer == 0 ? p.dbg_h1 : p.dbg_h2;
+        const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
 #pragma unroll 1
-        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
-          const int c = sub * kChunksPerWarp + cc;
+        for (int cc = 0; cc < kSteps; ++cc) {
+          const int c = cc * kSub + sub, part = c >> 1;
+          mbar_wait(&d_ready[part], layer, 7 + layer);  // layer 0 / 1 are the 1st / 2nd completion of d_ready per tile
+          tc_fence_after();
           uint32_t r[32], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -197,7 +220,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
             pk[j] = pack_bf16(v0, v1);
           }
-          tmem_st16(tmem_a + c * 16, pk);
+          tmem_st16(ta + c * 16, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[part]);
           if (dbg != nullptr && row < p.M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -207,27 +234,23 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
       }
       // head (one row per thread: the sub == 0 warps)
-      mbar_wait(mma_done, (g0 + 2) & 1, 9);
-      tc_fence_after();
       if (sub == 0) {
+        mbar_wait(head_ready, it & 1, 9);
+        tc_fence_after();
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(head_done);  // the head is in registers: layer 0 of the next tile may overwrite D
         if (row < p.M) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < p.A) p.out[row * p.A + j] = __uint_as_float(r[j]) + s_b2[j];
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(epi_done);
     }
   }
   tc_fence_before();

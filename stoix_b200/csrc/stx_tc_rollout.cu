@@ -68,7 +68,8 @@ struct Params {
 __global__ void __launch_bounds__(kThreads, 1)
     tc_rollout_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET (not through an integer cast) so that the compiler keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   float* s_b0 = reinterpret_cast<float*>(smem + kOffBias);
   float* s_b1 = s_b0 + 256;
@@ -77,9 +78,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 2;
   uint64_t* w_full = bars + 4;
-  uint64_t* mma_done = bars + 5;
-  uint64_t* epi_done = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* d_ready = bars + 5;      // [4] MMA -> epilogue: 64-column part p of the current layer's accumulator is complete
+  uint64_t* chunk_done = bars + 9;   // [4] epilogue -> MMA: part p consumed and its slice of the next A operand written
+  uint64_t* head_ready = bars + 13;  // logits complete
+  uint64_t* head_done = bars + 14;   // logits read out of tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tile_row0 = (int64_t)blockIdx.x * kTileM;
 
@@ -89,8 +92,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(w_full, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(epi_done, 8);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&d_ready[i], 1);
+      mbar_init(&chunk_done[i], 8);  // 4 lane quarters x 2 chunks of 32 columns
+    }
+    mbar_init(head_ready, 1);
+    mbar_init(head_done, 4);
     fence_barrier_init();
     tma_prefetch_desc(&tmW0);
     tma_prefetch_desc(&tmW1);
@@ -226,63 +233,79 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (hf == 0) p.run_return[e] = run_ret, p.run_length[e] = run_len;
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_n256 = idesc_bf16(128, 256, 0, 1);
+    // Every 256-wide GEMM is issued as four N=64 column parts; part p of the NEXT layer only needs D part p consumed
+    // and the K-chunks of its A operand written (chunk_done[]), so the tensor pipe trails the epilogue part by part
+    // (same scheme as K3a in stx_tc_ppo.cu).  h1 and h2 live in separate TMEM regions for that reason.
+    constexpr uint32_t idesc_n64 = idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t idesc_n16 = idesc_bf16(128, 16, 0, 1);
-    const uint32_t tmem_d = tmem, tmem_a = tmem + 256;
+    const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
     mbar_wait(w_full, 0, 31);
     for (int t = 0; t < p.T; ++t) {
       const int s = t & 1;
-      const int g0 = 3 * t;
       mbar_wait(&x_full[s], (t >> 1) & 1, 32);
-      if (g0 > 0) mbar_wait(epi_done, (g0 - 1) & 1, 33);
+      if (t > 0) mbar_wait(head_done, (t - 1) & 1, 33);  // the logits of step t-1 have left D columns 0..15
       tc_fence_after();
       if (elect_one()) {
         const uint32_t xa = sbase + kOffX + s * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_ss(tmem_d, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B), smem_desc(sbase + kOffW0 + k * 2048, 8192, 1024, SWIZZLE_128B),
-                 idesc_n256, k > 0);
+        for (int pt = 0; pt < 4; ++pt) {  // layer 0 (all of D is free: E1 of the previous step was waited for below)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_d + pt * 64, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
+                   smem_desc(sbase + kOffW0 + pt * 8192 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_n64, k > 0);
+          mma_commit(&d_ready[pt]);
+        }
         mma_commit(&x_empty[s]);
-        mma_commit(mma_done);
       }
       __syncwarp();
-      mbar_wait(epi_done, g0 & 1, 34);
-      tc_fence_after();
-      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          mma_ts(tmem_d, tmem_a + k * 8, smem_desc(sbase + kOffW1 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_n256, k > 0);
-        mma_commit(mma_done);
-      }
-      __syncwarp();
-      mbar_wait(epi_done, (g0 + 1) & 1, 35);
-      tc_fence_after();
-      if (elect_one()) {
+      for (int j = 0; j < 4; ++j) {  // layer 1, trailing E0
+        mbar_wait(&chunk_done[j], 0, 34);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          mma_ts(tmem_d, tmem_a + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_n16, k > 0);
-        mma_commit(mma_done);
+          for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll
+            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
+              mma_ts(tmem_d + pt * 64, tmem_a1 + k * 8, smem_desc(sbase + kOffW1 + pt * 32768 + k * 2048, 32768, 1024, SWIZZLE_128B),
+                     idesc_n64, k > 0);
+            if (j == 3) mma_commit(&d_ready[pt]);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // head, trailing E1 (columns 0..15 are free after its first part)
+        mbar_wait(&chunk_done[j], 1, 35);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 4 * j; k < 4 * j + 4; ++k)
+            mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_n16, k > 0);
+          if (j == 3) mma_commit(head_ready);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ===================== epilogue warps =====================
+    // step cc of a layer epilogue: chunk 2cc (half-0 warps) and 2cc+1 (half-1 warps) = the 64-column part cc
     const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t tmem_d = tmem + lane_addr, tmem_a = tmem + lane_addr + 256;
+    const uint32_t tmem_d = tmem + lane_addr, tmem_a1 = tmem + lane_addr + 256, tmem_a2 = tmem + lane_addr + 384;
     const int64_t e = tile_row0 + q * 32 + lane;
     const uint64_t call0 = p.cat_offset + (p.cat_counter ? *p.cat_counter : 0ull);
     const uint2 ckey = make_uint2((uint32_t)p.cat_seed, (uint32_t)(p.cat_seed >> 32));
     for (int t = 0; t < p.T; ++t) {
-      const int g0 = 3 * t;
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(mma_done, (g0 + layer) & 1, 36 + layer);
-        tc_fence_after();
         const float* bias = layer == 0 ? s_b0 : s_b1;
+        const uint32_t ta = layer == 0 ? tmem_a1 : tmem_a2;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
-          const int c = half * 4 + cc;
+          const int c = cc * 2 + half;
+          mbar_wait(&d_ready[cc], layer, 36 + layer);  // layer 0 / 1 are the 1st / 2nd completion of d_ready per step
+          tc_fence_after();
           uint32_t r[32], pk[16];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -292,19 +315,22 @@ __global__ void __launch_bounds__(kThreads, 1)
             const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
             pk[j] = pack_bf16(v0, v1);
           }
-          tmem_st16(tmem_a + c * 16, pk);
+          tmem_st16(ta + c * 16, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[cc]);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
       }
-      mbar_wait(mma_done, (g0 + 2) & 1, 38);
-      tc_fence_after();
       if (half == 0) {
+        mbar_wait(head_ready, t & 1, 38);
+        tc_fence_after();
         uint32_t r[16];
         tmem_ld16(tmem_d, r);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(head_done);  // the logits are in registers: layer 0 of the next step may overwrite D
         const int A = p.A;
         float z[16], zmax = -INFINITY;
 #pragma unroll
@@ -339,9 +365,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         p.action[o] = a;
         p.log_prob[o] = za - lse;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(epi_done);
     }
   }
   tc_fence_before();
