@@ -185,6 +185,31 @@ int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const Stx
                             float* grad_arena, float* metrics, int precision, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* One whole optimiser step on a minibatch = stx_ppo_minibatch_grads + stx_clip_adam_step (the body of
+ * _update_minibatch, ff_ppo.py:184-284) with the gradient reduction and the optimiser fused into one launch:
+ * the thread that reduces a gradient entry keeps it in a register, the blocks meet once at a grid barrier
+ * for the two global norms, and the same thread applies clip + Adam to that entry.  STX_PREC_BF16 only,
+ * single shard / single device (the gradients are overwritten, hyper->overwrite_grads is ignored);
+ * opt->nseg must be 2 with segment 0 = actor arena and segment 1 = critic arena.  Same results as the
+ * two separate calls (same reduction orders). */
+typedef struct StxFusedAdam {
+  float* param_arena;
+  float* mu;
+  float* nu;
+  int32_t* counts;          /* int32[2*nseg] device */
+  const StxAdamSeg* segs;   /* DEVICE pointer */
+  int32_t nseg;
+  int32_t reserved;
+  StxAdamHyper hyper;       /* prenorm is ignored */
+  void* params_bf16;        /* nullable */
+  float* gnorm_out;         /* nullable, float[nseg] */
+  void* scratch;            /* >= stx_adam_scratch_bytes(), zeroed once */
+} StxFusedAdam;
+int stx_ppo_minibatch_update(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* batch,
+                             int64_t mb_off, int64_t mb, const StxPpoHyper* hyper, float grad_weight,
+                             float* grad_arena, float* metrics, void* workspace, size_t workspace_bytes,
+                             const StxFusedAdam* opt, void* stream);
+
 /* Forward values of the two reference loss utilities (stoix/utils/loss.py:17-32 ppo_clip_loss,
  * :68-78 clipped_value_loss) over n elements; out[0] = mean.  scratch >= stx_loss_scratch_bytes(),
  * zeroed once.  (The training path uses the fused stx_ppo_minibatch_grads instead.) */

@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(kAdamThreads)
   __shared__ float s_gs[kAdamMaxSegs], s_bc1[kAdamMaxSegs], s_bc2[kAdamMaxSegs], s_lr[kAdamMaxSegs], s_gn[kAdamMaxSegs];
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
+  griddep_launch();
+  griddep_wait();  // gradients (and, with PRENORM, their sum-of-squares partials) come from the previous kernel
   if ((int)threadIdx.x < nseg) s_seg[threadIdx.x] = segs[threadIdx.x];
   __syncthreads();
 
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(kAdamThreads)
     const int s = warp;
     const unsigned int nparts = PRENORM ? (unsigned int)__ldcg(&scratch->n_partials) : gridDim.x;
     const double* vp = partials + (int64_t)s * nparts;
+    int32_t cnt_adam = 0, cnt_sched = 0;  // requested together with the partials (one round trip, not two)
+    if (lane == 0) cnt_adam = counts[2 * s], cnt_sched = counts[2 * s + 1];
     double part = 0.0;
     for (unsigned int b = lane; b < nparts; b += 32) part += __ldcg(vp + b);
     part = warp_sum(part);
@@ -181,10 +185,10 @@ __global__ void __launch_bounds__(kAdamThreads)
       const float g_norm = (float)sqrt(ss);
       // optax.clip_by_global_norm: trigger = g_norm < max_norm
       const float clip = (g_norm < s_seg[s].max_grad_norm) ? 1.0f : s_seg[s].max_grad_norm / g_norm;
-      const int32_t c = counts[2 * s] + 1;
+      const int32_t c = cnt_adam + 1;
       float lr = s_seg[s].init_lr;
       if (h.decay) {
-        const int32_t k = counts[2 * s + 1] / h.steps_per_update;  // floor division, utils/training.py:25
+        const int32_t k = cnt_sched / h.steps_per_update;  // floor division, utils/training.py:25
         lr = s_seg[s].init_lr * (1.0f - (float)k / (float)h.num_updates);
       }
       s_gs[s] = h.grad_scale * clip;
@@ -298,13 +302,13 @@ extern "C" int stx_clip_adam_step(float* param_arena, const float* grad_arena, f
   const int grid = kNumSMs;
   const PeerSync none{};
   if (hyper->prenorm)
-    clip_adam_kernel<true, false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
-        param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
-        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch), none);
+    STX_CUDA_OK(launch_pdl(clip_adam_kernel<true, false>, dim3(grid), dim3(kAdamThreads), 0, (cudaStream_t)stream, param_arena, grad_arena,
+                           mu, nu, counts, segs, nseg, *hyper, reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out,
+                           reinterpret_cast<AdamScratch*>(scratch), none));
   else
-    clip_adam_kernel<false, false><<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
-        param_arena, grad_arena, mu, nu, counts, segs, nseg, *hyper,
-        reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch), none);
+    STX_CUDA_OK(launch_pdl(clip_adam_kernel<false, false>, dim3(grid), dim3(kAdamThreads), 0, (cudaStream_t)stream, param_arena, grad_arena,
+                           mu, nu, counts, segs, nseg, *hyper, reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out,
+                           reinterpret_cast<AdamScratch*>(scratch), none));
   STX_LAUNCH_OK();
   (void)adam_grid;
   return STX_OK;
@@ -343,9 +347,9 @@ extern "C" int stx_allreduce_clip_adam_step(float* param_arena, const float* con
   ps.local_gen = reinterpret_cast<unsigned int*>(sc + base);
   ps.local_ready = reinterpret_cast<unsigned int*>(sc + base + 8);
   ps.gsum = gsum, ps.world = world, ps.rank = rank;
-  clip_adam_kernel<false, true><<<kNumSMs, kAdamThreads, 0, (cudaStream_t)stream>>>(
-      param_arena, gsum, mu, nu, counts, segs, nseg, *hyper, reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out,
-      reinterpret_cast<AdamScratch*>(scratch), ps);
+  STX_CUDA_OK(launch_pdl(clip_adam_kernel<false, true>, dim3(kNumSMs), dim3(kAdamThreads), 0, (cudaStream_t)stream, param_arena,
+                         static_cast<const float*>(gsum), mu, nu, counts, segs, nseg, *hyper,
+                         reinterpret_cast<__nv_bfloat16*>(params_bf16), gnorm_out, reinterpret_cast<AdamScratch*>(scratch), ps));
   STX_LAUNCH_OK();
   return STX_OK;
 }

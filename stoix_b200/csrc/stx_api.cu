@@ -1,5 +1,6 @@
 // Library-wide entry points: version and thread-local error string.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -11,6 +12,10 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = !(getenv("STX_PDL") && atoi(getenv("STX_PDL")) == 0);
+  return on;
+}
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

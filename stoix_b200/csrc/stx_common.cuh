@@ -42,6 +42,28 @@ void count_launch();
     STX_CUDA_OK(cudaPeekAtLastError());  \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The optimiser step is a strict chain of short kernels (K3a -> K3b -> reduce -> K4, 64 times per update).  A kernel
+// launched through launch_pdl() may become resident while its stream predecessor is still running (its prologue --
+// barrier init, TMEM allocation, smem clearing -- overlaps the predecessor's tail and the launch latency is hidden);
+// it MUST execute griddep_wait() before touching any global memory the predecessor chain reads or writes.
+// STX_PDL=0 in the environment launches the same kernels fully serialised (then griddep_wait() is a no-op).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs

@@ -14,7 +14,7 @@ size_t tc_ppo_workspace_bytes(const StxMlp* actor, const StxMlp* critic, int64_t
 int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* batch,
                            int64_t mb_off, int64_t mb, const StxPpoHyper* hyper, float grad_weight,
                            float* grad_arena, float* metrics, void* ws, size_t ws_bytes,
-                           cudaStream_t st);
+                           cudaStream_t st, const StxFusedAdam* opt);
 
 namespace {
 
@@ -270,6 +270,30 @@ extern "C" size_t stx_ppo_workspace_bytes(const StxMlp* actor, const StxMlp* cri
   return (a > c ? a : c);
 }
 
+extern "C" int stx_ppo_minibatch_update(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* b, int64_t mb_off, int64_t mb,
+                                        const StxPpoHyper* h, float grad_weight, float* grad_arena, float* metrics, void* workspace,
+                                        size_t workspace_bytes, const StxFusedAdam* opt, void* stream) {
+  if (int rc = check_mlp(actor, "stx_ppo_minibatch_update(actor)")) return rc;
+  if (int rc = check_mlp(critic, "stx_ppo_minibatch_update(critic)")) return rc;
+  STX_REQUIRE(b && h && grad_arena && metrics && workspace && opt, STX_E_ARG, "stx_ppo_minibatch_update: null pointer");
+  STX_REQUIRE(b->obs && b->action && b->log_prob && b->value && b->advantages && b->targets, STX_E_ARG,
+              "stx_ppo_minibatch_update: null batch field");
+  STX_REQUIRE(opt->param_arena && opt->mu && opt->nu && opt->counts && opt->segs && opt->scratch, STX_E_ARG,
+              "stx_ppo_minibatch_update: null optimiser field");
+  STX_REQUIRE(opt->nseg == 2, STX_E_SHAPE, "stx_ppo_minibatch_update: nseg=%d (segment 0 = actor arena, 1 = critic arena)", opt->nseg);
+  STX_REQUIRE(opt->hyper.steps_per_update > 0 && opt->hyper.num_updates > 0, STX_E_ARG,
+              "stx_ppo_minibatch_update: steps_per_update/num_updates must be positive");
+  STX_REQUIRE(mb > 0 && mb_off >= 0 && mb_off + mb <= b->B, STX_E_SHAPE, "stx_ppo_minibatch_update: minibatch [%lld,%lld) outside batch %lld",
+              (long long)mb_off, (long long)(mb_off + mb), (long long)b->B);
+  STX_REQUIRE(actor->sizes[0] == critic->sizes[0], STX_E_SHAPE, "actor/critic input dims differ");
+  STX_REQUIRE(critic->sizes[critic->n_layers] == 1, STX_E_SHAPE, "critic head must be scalar");
+  STX_REQUIRE(!h->standardize_advantages || b->adv_stats, STX_E_ARG, "standardize_advantages needs adv_stats");
+  STX_REQUIRE(workspace_bytes >= stx_ppo_workspace_bytes(actor, critic, mb, STX_PREC_BF16), STX_E_WORKSPACE,
+              "stx_ppo_minibatch_update: workspace %zu < %zu", workspace_bytes, stx_ppo_workspace_bytes(actor, critic, mb, STX_PREC_BF16));
+  return tc_ppo_minibatch_grads(actor, critic, b, mb_off, mb, h, grad_weight, grad_arena, metrics, workspace, workspace_bytes,
+                                (cudaStream_t)stream, opt);
+}
+
 extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic,
                                        const StxPpoBatch* b, int64_t mb_off, int64_t mb,
                                        const StxPpoHyper* h, float grad_weight, float* grad_arena,
@@ -293,7 +317,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
               stx_ppo_workspace_bytes(actor, critic, mb, precision));
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == STX_PREC_BF16)
-    return tc_ppo_minibatch_grads(actor, critic, b, mb_off, mb, h, grad_weight, grad_arena, metrics, workspace, workspace_bytes, st);
+    return tc_ppo_minibatch_grads(actor, critic, b, mb_off, mb, h, grad_weight, grad_arena, metrics, workspace, workspace_bytes, st, nullptr);
   STX_REQUIRE(precision == STX_PREC_F32, STX_E_UNSUPPORTED, "precision=%d", precision);
 
   int64_t aoff, coff, total;

@@ -199,7 +199,22 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     tma_prefetch_desc(tmW0);
     tma_prefetch_desc(tmW1);
   }
+  griddep_launch();  // K3b cannot co-reside with this CTA anyway; lets its launch be queued early
   if (warp == kFbMmaWarp) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 4 * 528; i += fb_threads(NEPI)) s_db[i] = 0.f;
+  griddep_wait();  // everything above overlapped the previous optimiser kernel; the weights below are its output
+  // Start every long-latency fetch of the prologue at once: the 160 KB of W0/W1 (TMA), the first shuffle indices of the
+  // gather and loss-input rows, then the W2 / bias staging below; all of them are in flight together.
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(w_full, 32768 + 131072);
+    for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
+    for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
+  }
+  int32_t idx_first = 0;  // producers: row of tile 0 owned by this thread; epilogue (sub 0): its loss-input row of tile 0
+  if (p.idx != nullptr && my_tiles > 0) {
+    if (warp < 4) idx_first = p.idx[(int64_t)cta_in_net * kTileM + threadIdx.x];
+    else if (warp >= 5 && warp < 9) idx_first = p.idx[(int64_t)cta_in_net * kTileM + (warp & 3) * 32 + lane];
+  }
   {
     // one thread per W2 row: all of its (<=16) loads are independent and in flight together
     uint8_t* w2s = smem + kOffW2;
@@ -221,7 +236,6 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     }
     for (int i = threadIdx.x; i < 256; i += fb_threads(NEPI)) s_b0[i] = net.b0[i], s_b1[i] = net.b1[i];
     if (threadIdx.x < 16) s_b2[threadIdx.x] = threadIdx.x < net.A ? net.b2[threadIdx.x] : 0.f;
-    for (int i = threadIdx.x; i < 4 * 528; i += fb_threads(NEPI)) s_db[i] = 0.f;
     fence_async_proxy();
   }
   tc_fence_before();
@@ -233,19 +247,16 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
   float m_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actor_loss, entropy, value_loss, adv, pred value, target
 
   if (warp < 4) {
-    // ===================== producers: weights by TMA, X rows gathered one row per thread =====================
-    if (threadIdx.x == 0) {
-      mbar_arrive_expect_tx(w_full, 32768 + 131072);
-      for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
-      for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
-    }
+    // ===================== producers: X rows gathered one row per thread =====================
     const int dchunks = p.D >> 3;  // 16-byte chunks per observation row
     const int r = threadIdx.x;     // row of the tile owned by this thread
+    int32_t gidx = idx_first;      // shuffle index of this thread's row: fetched one tile ahead, kept raw until used
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + r;
-      const int64_t src = p.idx ? (int64_t)p.idx[mrow] : p.row0 + mrow;
+      const int64_t src = p.idx ? (int64_t)gidx : p.row0 + mrow;
+      if (p.idx && it + 1 < my_tiles) gidx = p.idx[mrow + (int64_t)ncta * kTileM];
       uint4 v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c)  // 8 independent 16-byte loads in flight per thread
@@ -372,8 +383,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     // source row of this thread's row in the NEXT tile: loaded one tile ahead so that the dependent per-row
     // loads below never wait on the index (two chained DRAM latencies would otherwise open every tile)
     // (kept RAW: a conversion right behind the load would stall this in-order warp for the full memory latency)
-    int32_t idx_next = 0;
-    if (sub == 0 && my_tiles > 0 && p.idx) idx_next = p.idx[(int64_t)cta_in_net * kTileM + q * 32 + lane];
+    int32_t idx_next = idx_first;  // (tile 0: requested in the prologue)
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
@@ -607,11 +617,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     tma_prefetch_desc(&maps.a[j]);
     tma_prefetch_desc(&maps.b[j]);
   }
+  griddep_launch();
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_wait();  // the activations are K3a's output; the partials written below were read by the previous reduce
 
   if (warp == 0) {
     if (elect_one()) {
@@ -715,12 +727,39 @@ struct RedParams {
 constexpr int kRedThreads = 288;  // x 592 blocks >= the ~168k gradient entries of the benchmark networks: one element per thread
 constexpr int kRedMaxBlocks = 4 * kNumSMs;  // the optimiser scratch holds 8 x 148 doubles = 2 segments x 592 block partials
 
+// Optimiser context of the fused variant (stx_ppo_minibatch_update): clip_by_global_norm + Adam of stx_adam.cu applied
+// by the thread that reduced the gradient entry.  scratch layout = stx_adam.cu's AdamScratch.
+struct FusedOpt {
+  float* P;
+  float* MU;
+  float* NU;
+  int32_t* counts;
+  const StxAdamSeg* segs;
+  StxAdamHyper h;
+  __nv_bfloat16* P16;
+  float* gnorm_out;
+  unsigned long long* arrive;   // grid-barrier ticket (monotonic)
+  unsigned long long* finish;   // last-block ticket (monotonic)
+};
+
 // Fixed-order reduction of the per-CTA partials into the gradient arena.  One launch, every segment
 // concurrently; 4 independent accumulators per element for load-level parallelism; the association order
 // is fixed => run-to-run deterministic gradients.  Optionally leaves the per-block sum of squares of the
 // reduced gradient for the fused optimiser (which can then skip its own norm pass and grid barrier).
-__global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams p, float* __restrict__ grad) {
+//
+// FUSED: every thread owns at most ONE gradient entry (host-checked) and keeps it in a register; after the per-block
+// sum-of-squares partials are published the blocks meet at a software grid barrier (all blocks are co-resident: the
+// host checks the occupancy), every block re-reduces the partials in the fixed order of clip_adam_kernel<PRENORM>
+// and the thread applies clip + Adam + the bf16 shadow update to its entry: K4 without its launch, its gradient
+// re-read and its own ramp-up.
+template <bool FUSED>
+__global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams p, float* __restrict__ grad, const FusedOpt f) {
+  griddep_launch();
+  griddep_wait();
   double sq0 = 0.0, sq1 = 0.0;
+  int64_t my_dst = -1;  // FUSED: arena index, value and optimiser segment of this thread's entry
+  float my_g = 0.f;
+  int my_net = 0;
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < p.total_items; gi += gridDim.x * blockDim.x) {
     int s = 0, i = gi;
     while (i >= p.seg[s].items) i -= p.seg[s].items, ++s;
@@ -736,21 +775,35 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
         r = i / g.cols, c = i % g.cols;
         src = g.part + (int64_t)r * g.src_ld + c;
       }
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // many short independent chains: this kernel is latency-bound
+      // latency-bound (the partials were evicted by the activation traffic: every round trip goes to DRAM): 8 independent
+      // loads in flight per thread and round trip, 4 accumulation chains in a fixed order.  (16 per round trip with
+      // predicated tails measured 3x SLOWER: the batch no longer fits the scoreboard/registers the compiler allots.)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const int64_t S = g.part_stride;
       int k = 0;
-      for (; k + 4 <= g.n_part; k += 4) {
-        a0 += src[(int64_t)k * g.part_stride];
-        a1 += src[(int64_t)(k + 1) * g.part_stride];
-        a2 += src[(int64_t)(k + 2) * g.part_stride];
-        a3 += src[(int64_t)(k + 3) * g.part_stride];
+      for (; k + 8 <= g.n_part; k += 8) {
+        const float* q = src + (int64_t)k * S;
+        const float v0 = __ldcg(q), v1 = __ldcg(q + S), v2 = __ldcg(q + 2 * S), v3 = __ldcg(q + 3 * S);
+        const float v4 = __ldcg(q + 4 * S), v5 = __ldcg(q + 5 * S), v6 = __ldcg(q + 6 * S), v7 = __ldcg(q + 7 * S);
+        a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+        a0 += v4, a1 += v5, a2 += v6, a3 += v7;
       }
-      for (; k < g.n_part; ++k) a0 += src[(int64_t)k * g.part_stride];
+      if (k < g.n_part) {  // up to 7 left: one more batch of independent (predicated) loads
+        const float* q = src + (int64_t)k * S;
+        const int n = g.n_part - k;
+        const float v0 = __ldcg(q), v1 = n > 1 ? __ldcg(q + S) : 0.f, v2 = n > 2 ? __ldcg(q + 2 * S) : 0.f;
+        const float v3 = n > 3 ? __ldcg(q + 3 * S) : 0.f, v4 = n > 4 ? __ldcg(q + 4 * S) : 0.f, v5 = n > 5 ? __ldcg(q + 5 * S) : 0.f;
+        const float v6 = n > 6 ? __ldcg(q + 6 * S) : 0.f;
+        a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+        a0 += v4, a1 += v5, a2 += v6;
+      }
       float* dst = grad + g.dst_off + (g.transpose ? (int64_t)c * g.dst_ld + r : (int64_t)r * g.dst_ld + c);
       float o = p.weight * ((a0 + a1) + (a2 + a3));
       if (!p.overwrite) o += *dst;
       *dst = o;
       if (g.net) sq1 += (double)o * o;
       else sq0 += (double)o * o;
+      if (FUSED) my_dst = dst - grad, my_g = o, my_net = g.net;
     }
   }
   if (p.sumsq != nullptr) {  // only meaningful with overwrite (then o is the whole gradient)
@@ -766,6 +819,71 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
     float acc = 0.f;
     for (int k = 0; k < p.n_cta_total; ++k) acc += p.metric_part[(int64_t)k * 8 + threadIdx.x];
     p.metrics[threadIdx.x] += p.weight * acc * p.inv_mb;
+  }
+  if (FUSED) {
+    __shared__ StxAdamSeg s_seg[2];
+    __shared__ float s_gs[2], s_bc1[2], s_bc2[2], s_lr[2], s_gn[2];
+    if (threadIdx.x < 2) s_seg[threadIdx.x] = f.segs[threadIdx.x];
+    // ---- grid barrier (partials of every block are published above) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long t = atomicAdd(f.arrive, 1ull);
+      const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
+      while (*reinterpret_cast<volatile unsigned long long*>(f.arrive) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    // ---- norms: warp s <-> segment s, same summation order as clip_adam_kernel<PRENORM> ----
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+      const int s = warp;
+      const double* vp = p.sumsq + (int64_t)s * gridDim.x;
+      double part = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) part += __ldcg(vp + b);
+      part = warp_sum(part);
+      if (lane == 0) {
+        const double ss = part * (double)f.h.grad_scale * (double)f.h.grad_scale;
+        const float g_norm = (float)sqrt(ss);
+        const float clip = (g_norm < s_seg[s].max_grad_norm) ? 1.0f : s_seg[s].max_grad_norm / g_norm;
+        const int32_t c = f.counts[2 * s] + 1;
+        float lr = s_seg[s].init_lr;
+        if (f.h.decay) {
+          const int32_t k = f.counts[2 * s + 1] / f.h.steps_per_update;  // floor division, utils/training.py:25
+          lr = s_seg[s].init_lr * (1.0f - (float)k / (float)f.h.num_updates);
+        }
+        s_gs[s] = f.h.grad_scale * clip;
+        s_bc1[s] = 1.0f - powf(f.h.b1, (float)c);
+        s_bc2[s] = 1.0f - powf(f.h.b2, (float)c);
+        s_lr[s] = lr;
+        s_gn[s] = g_norm;
+      }
+    }
+    __syncthreads();
+    if (my_dst >= 0) {
+      const int s = my_net;
+      const float ge = my_g * s_gs[s];
+      const float me = f.h.b1 * f.MU[my_dst] + (1.0f - f.h.b1) * ge;
+      const float ve = f.h.b2 * f.NU[my_dst] + (1.0f - f.h.b2) * ge * ge;
+      const float u = (me / s_bc1[s]) / (sqrtf(ve / s_bc2[s]) + f.h.eps);
+      const float pn = f.P[my_dst] - s_lr[s] * u;
+      f.MU[my_dst] = me, f.NU[my_dst] = ve, f.P[my_dst] = pn;
+      if (f.P16) f.P16[my_dst] = __float2bfloat16_rn(pn);
+    }
+    // the step counters are advanced by whichever block finishes last (every block has read them by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long t = atomicAdd(f.finish, 1ull);
+      if (t % gridDim.x == gridDim.x - 1) {
+        for (int s = 0; s < 2; ++s) {
+          f.counts[2 * s] += 1;
+          f.counts[2 * s + 1] += 1;
+          if (f.gnorm_out) f.gnorm_out[s] = s_gn[s];
+        }
+      }
+    }
   }
 }
 
@@ -820,7 +938,7 @@ size_t tc_ppo_workspace_bytes(const StxMlp* a, const StxMlp* c, int64_t mb) {
 
 int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxPpoBatch* b, int64_t mb_off, int64_t mb,
                            const StxPpoHyper* h, float grad_weight, float* grad_arena, float* metrics, void* ws_raw, size_t,
-                           cudaStream_t st) {
+                           cudaStream_t st, const StxFusedAdam* opt) {
   using namespace tc;
   STX_REQUIRE(tc_ppo_shape_ok(actor) && tc_ppo_shape_ok(critic), STX_E_SHAPE,
               "STX_PREC_BF16 PPO kernels need MLP [D<=64 (mult of 8), 256, 256, head<=16]");
@@ -866,7 +984,8 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     attr_set = true;
   }
   // 8 epilogue warps: 16 (two parts per step, 80 registers) measured 5 % slower (profiles/README.md)
-  tc_ppo_fwd_bwd_kernel<8><<<2 * kCtaPerNet, fb_threads(8), kFbSmemBytes, st>>>(tmW0[0], tmW1[0], tmW0[1], tmW1[1], fp);
+  STX_CUDA_OK(launch_pdl(tc_ppo_fwd_bwd_kernel<8>, dim3(2 * kCtaPerNet), dim3(fb_threads(8)), kFbSmemBytes, st, tmW0[0], tmW1[0], tmW0[1],
+                         tmW1[1], fp));
   STX_LAUNCH_OK();
 
   // ---- K3b ----
@@ -893,7 +1012,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     cta += kDwCtaW0, ++jn;
   }
   dp.n_jobs = jn;
-  tc_dw_kernel<<<cta, kDwThreads, kDwSmemBytes, st>>>(maps, dp);
+  STX_CUDA_OK(launch_pdl(tc_dw_kernel, dim3(cta), dim3(kDwThreads), kDwSmemBytes, st, maps, dp));
   STX_LAUNCH_OK();
 
   // ---- reduce ----
@@ -923,13 +1042,33 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   rp.n_seg = sidx;
   rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
   rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
-  rp.overwrite = h->overwrite_grads;
+  rp.overwrite = opt ? 1 : h->overwrite_grads;
   // side output for the fused optimiser: partials[seg][block] right after the 16-byte header of its scratch
-  rp.sumsq = (h->overwrite_grads && h->adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->adam_scratch) + 16) : nullptr;
-  rp.sumsq_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->adam_scratch) + 8);
+  void* adam_scratch = opt ? opt->scratch : h->adam_scratch;
+  rp.sumsq = (rp.overwrite && adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(adam_scratch) + 16) : nullptr;
+  rp.sumsq_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(adam_scratch) + 8);
   int red_blocks = (rp.total_items + kRedThreads - 1) / kRedThreads;  // one item per thread, blocks spread over all SMs
   if (red_blocks > kRedMaxBlocks) red_blocks = kRedMaxBlocks;
-  tc_reduce_kernel<<<red_blocks, kRedThreads, 0, st>>>(rp, grad_arena);
+  FusedOpt fo{};
+  if (opt) {
+    // one entry per thread and all blocks co-resident (grid barrier), else the caller must use the two-call path
+    static int blocks_per_sm = -1;
+    if (blocks_per_sm < 0) STX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, tc_reduce_kernel<true>, kRedThreads, 0));
+    STX_REQUIRE(rp.total_items <= red_blocks * kRedThreads && red_blocks <= blocks_per_sm * kNumSMs, STX_E_SHAPE,
+                "stx_ppo_minibatch_update: %d gradient entries do not fit one co-resident wave (%d blocks x %d threads, %d blocks/SM)",
+                rp.total_items, red_blocks, kRedThreads, blocks_per_sm);
+    fo.P = opt->param_arena, fo.MU = opt->mu, fo.NU = opt->nu, fo.counts = opt->counts, fo.segs = opt->segs, fo.h = opt->hyper;
+    fo.P16 = reinterpret_cast<__nv_bfloat16*>(opt->params_bf16), fo.gnorm_out = opt->gnorm_out;
+    char* sc = reinterpret_cast<char*>(opt->scratch);
+    // own ticket words (stx_adam.cu keeps its barrier / last-block tickets for a 148-block grid in the same scratch: the
+    // modulo arithmetic of a ticket is only valid for one grid size)
+    char* tail = sc + 16 + sizeof(double) * 8 * kNumSMs;  // = sizeof(AdamScratch) + partials; 64 spare bytes follow
+    fo.arrive = reinterpret_cast<unsigned long long*>(tail + 24);
+    fo.finish = reinterpret_cast<unsigned long long*>(tail + 32);
+    STX_CUDA_OK(launch_pdl(tc_reduce_kernel<true>, dim3(red_blocks), dim3(kRedThreads), 0, st, rp, grad_arena, fo));
+  } else {
+    STX_CUDA_OK(launch_pdl(tc_reduce_kernel<false>, dim3(red_blocks), dim3(kRedThreads), 0, st, rp, grad_arena, fo));
+  }
   STX_LAUNCH_OK();
   return STX_OK;
 }

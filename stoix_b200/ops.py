@@ -297,6 +297,42 @@ def ppo_minibatch_grads(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tens
     )
 
 
+def ppo_minibatch_update(actor: MlpSpec, critic: MlpSpec, param_arena: torch.Tensor, batch: PpoBatch,
+                         mb_off: int, mb: int, clip_eps: float, ent_coef: float, vf_coef: float,
+                         standardize: bool, grad_arena: torch.Tensor, metrics: torch.Tensor,
+                         workspace: torch.Tensor, plan: "AdamPlan", mu: torch.Tensor, nu: torch.Tensor,
+                         param_arena_bf16: torch.Tensor, grad_weight: float = 1.0, grad_scale: float = 1.0) -> None:
+    """One whole optimiser step on minibatch [mb_off, mb_off+mb) (ff_ppo.py:184-284): gradients of both losses,
+    clip_by_global_norm + Adam on both networks, bf16 shadow refresh; the gradient reduction and the optimiser share
+    one launch (stx_ppo_minibatch_update).  bf16 path, one shard, one device; `plan` must hold exactly the two
+    segments (actor arena, critic arena).  Same results as ppo_minibatch_grads(overwrite=True) + clip_adam_step."""
+    _need_cuda(param_arena, batch.obs, batch.action, batch.log_prob, batch.value, batch.advantages,
+               batch.targets, batch.adv_stats, batch.perm, grad_arena, metrics, workspace, mu, nu, param_arena_bf16)
+    if batch.action.dtype != torch.int32 or (batch.perm is not None and batch.perm.dtype != torch.int32):
+        raise StxError("ppo_minibatch_update: action / perm must be int32")
+    if batch.obs.dtype != torch.bfloat16:
+        raise StxError("ppo_minibatch_update: obs must be bfloat16 (STX_PREC_BF16 path)")
+    _, coff, total = arena_offsets(actor, critic)
+    if min(param_arena.numel(), grad_arena.numel(), mu.numel(), nu.numel(), param_arena_bf16.numel()) < total or metrics.numel() < 6:
+        raise StxError("ppo_minibatch_update: arena or metrics too small")
+    if plan.nseg != 2:
+        raise StxError("ppo_minibatch_update: the optimiser plan must have the two segments (actor, critic)")
+    lib = _lib.load()
+    a = actor.c_struct(param_arena, param_arena_bf16)
+    c = critic.c_struct(param_arena[coff:], param_arena_bf16[coff:])
+    b = batch.c_struct()
+    h = _lib.StxPpoHyper(float(clip_eps), float(ent_coef), float(vf_coef), int(bool(standardize)), 1, 0, None)
+    plan.hyper.grad_scale = float(grad_scale)
+    plan.hyper.prenorm = 0
+    opt = _lib.StxFusedAdam(_p(param_arena), _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg, 0, plan.hyper,
+                            _p(param_arena_bf16), _p(plan.gnorm), _p(plan.scratch))
+    _lib.check(
+        lib.stx_ppo_minibatch_update(C.byref(a), C.byref(c), C.byref(b), int(mb_off), int(mb), C.byref(h), float(grad_weight),
+                                     _p(grad_arena), _p(metrics), _p(workspace), workspace.numel(), C.byref(opt), _stream()),
+        "stx_ppo_minibatch_update",
+    )
+
+
 def _loss_value(fn_name: str, a, b, c, eps: float) -> torch.Tensor:
     dev = _need_cuda(a, b, c)
     if not (a.dtype == b.dtype == c.dtype == torch.float32) or not (a.numel() == b.numel() == c.numel()):

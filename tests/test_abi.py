@@ -45,6 +45,7 @@ def test_struct_layouts_match_c():
     assert ctypes.sizeof(_lib.StxAdamHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoBatch) == 72
+    assert ctypes.sizeof(_lib.StxFusedAdam) == 5 * 8 + 8 + 32 + 3 * 8
 
 
 def test_ops_refuse_cpu_tensors_and_missing_library(monkeypatch, tmp_path):
