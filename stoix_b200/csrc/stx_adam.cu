@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(kAdamThreads)
   // ---- phase 2 ----
   // PRENORM: the gradients are final at kernel entry, so the first item of the first two segments is requested
   // BEFORE the norm reduction: its loads overlap the (dependent) partials round trip.
+  // parameters, moments, gradients and the bf16 shadow (the next K3a's weights) stay L2-resident under the activation
+  // stream of the surrounding kernels: this kernel is a chain of dependent round trips
+  const uint64_t pol_keep = l2_evict_last();
   constexpr int kPf = 2;
   float4 pf_g[kPf], pf_m[kPf], pf_v[kPf], pf_p[kPf];
   if (PRENORM) {
@@ -162,10 +165,10 @@ __global__ void __launch_bounds__(kAdamThreads)
     for (int s = 0; s < kPf; ++s)
       if (s < nseg && gtid < s_seg[s].count / 4) {
         const int64_t o = s_seg[s].offset;
-        pf_g[s] = reinterpret_cast<const float4*>(G + o)[gtid];
-        pf_m[s] = reinterpret_cast<const float4*>(MU + o)[gtid];
-        pf_v[s] = reinterpret_cast<const float4*>(NU + o)[gtid];
-        pf_p[s] = reinterpret_cast<const float4*>(P + o)[gtid];
+        pf_g[s] = ld_hint(reinterpret_cast<const float4*>(G + o) + gtid, pol_keep);
+        pf_m[s] = ld_hint(reinterpret_cast<const float4*>(MU + o) + gtid, pol_keep);
+        pf_v[s] = ld_hint(reinterpret_cast<const float4*>(NU + o) + gtid, pol_keep);
+        pf_p[s] = ld_hint(reinterpret_cast<const float4*>(P + o) + gtid, pol_keep);
       }
   }
   // every block re-reduces the per-block partials in the same fixed order (warp s <-> segment s: lane-strided
@@ -213,9 +216,9 @@ __global__ void __launch_bounds__(kAdamThreads)
       if (PRENORM && s < kPf && i == gtid) {
         gv = pf_g[s < kPf ? s : 0], m = pf_m[s < kPf ? s : 0], v = pf_v[s < kPf ? s : 0], pv = pf_p[s < kPf ? s : 0];
       } else {
-        gv = reinterpret_cast<const float4*>(g)[i];
-        m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
-        pv = reinterpret_cast<float4*>(p)[i];
+        gv = ld_hint(reinterpret_cast<const float4*>(g) + i, pol_keep);
+        m = ld_hint(reinterpret_cast<const float4*>(mu) + i, pol_keep), v = ld_hint(reinterpret_cast<const float4*>(nu) + i, pol_keep);
+        pv = ld_hint(reinterpret_cast<const float4*>(p) + i, pol_keep);
       }
       float ge[4] = {gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs};
       float me[4] = {m.x, m.y, m.z, m.w}, ve[4] = {v.x, v.y, v.z, v.w}, pe[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -226,15 +229,15 @@ __global__ void __launch_bounds__(kAdamThreads)
         const float u = (me[k] / bc1) / (sqrtf(ve[k] / bc2) + h.eps);
         pe[k] = pe[k] - lr * u;
       }
-      reinterpret_cast<float4*>(mu)[i] = make_float4(me[0], me[1], me[2], me[3]);
-      reinterpret_cast<float4*>(nu)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
-      reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      st_hint(reinterpret_cast<float4*>(mu) + i, make_float4(me[0], me[1], me[2], me[3]), pol_keep);
+      st_hint(reinterpret_cast<float4*>(nu) + i, make_float4(ve[0], ve[1], ve[2], ve[3]), pol_keep);
+      st_hint(reinterpret_cast<float4*>(p) + i, make_float4(pe[0], pe[1], pe[2], pe[3]), pol_keep);
       if (P16) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(pe[0], pe[1]), hi = __floats2bfloat162_rn(pe[2], pe[3]);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(P16 + seg.offset)[i] = pk;
+        st_hint(reinterpret_cast<uint2*>(P16 + seg.offset) + i, pk, pol_keep);
       }
     }
     for (int64_t i = n4 * 4 + gtid; i < seg.count; i += gthreads) {

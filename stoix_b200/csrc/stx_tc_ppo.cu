@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t pol_stream = l2_evict_first();  // the activations are written once and read once (by K3b)
   const int which = (int)blockIdx.x < p.n_cta[0] ? 0 : 1;
   const FbNet& net = p.net[which];
   const int cta_in_net = which == 0 ? (int)blockIdx.x : (int)blockIdx.x - p.n_cta[0];
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
       if (which == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *tiled_ptr(p.xg, mrow, c, 8) = v[c];
+        for (int c = 0; c < 8; ++c) st_hint(tiled_ptr(p.xg, mrow, c, 8), v[c], pol_stream);
       }
       if (warp == 0) STX_STAMP(50);
       fence_async_proxy();
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
 #pragma unroll
           for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
-            *tiled_ptr(hout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            st_hint(tiled_ptr(hout, mrow, c * 4 + j, 32), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]), pol_stream);
         }
       }
       // ---------------- E2: head + loss + d(head) ----------------
@@ -472,8 +473,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(head_done);
         if (warp == 5) STX_STAMP(44);
-        *tiled_ptr(net.dz, mrow, 0, 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *tiled_ptr(net.dz, mrow, 1, 2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        st_hint(tiled_ptr(net.dz, mrow, 0, 2), make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+        st_hint(tiled_ptr(net.dz, mrow, 1, 2), make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
         // bias gradient of the head (off the critical path: G3 is already running): column sums over the 32 rows
         // of this warp; fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
         {
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *tiled_ptr(dout, mrow, c * 4 + j, 32) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            st_hint(tiled_ptr(dout, mrow, c * 4 + j, 32), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]), pol_stream);
           const float cs = warp_colsum32(dv, lane);
           dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
         }
@@ -627,6 +628,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
 
   if (warp == 0) {
     if (elect_one()) {
+      const uint64_t pol_stream = l2_evict_first();  // every activation tile is read exactly once
       for (int it = 0; it < my_chunks; ++it) {
         const int s = it % kDwStages;
         if (it >= kDwStages) mbar_wait(&empty[s], ((it / kDwStages) & 1) ^ 1, 20);
@@ -636,8 +638,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
         uint8_t* st = smem + s * kDwStageBytes;
         mbar_arrive_expect_tx(&full[s], stage_tx);
         // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
-        tma_load_2d(st, &maps.a[j], &full[s], r0 * 2, tile * 32);
-        tma_load_2d(st + 32768, &maps.b[j], &full[s], r0 * 2, tile * cgb);
+        tma_load_2d_hint(st, &maps.a[j], &full[s], r0 * 2, tile * 32, pol_stream);
+        tma_load_2d_hint(st + 32768, &maps.b[j], &full[s], r0 * 2, tile * cgb, pol_stream);
       }
     }
   } else if (warp == 1) {
@@ -666,6 +668,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // partial layout [N/4][256 rows][4]: the 32 lanes of a warp (= 32 consecutive rows) write 512 contiguous bytes
     float4* out = reinterpret_cast<float4*>(job.part + (int64_t)cta * 256 * job.N);
+    const uint64_t pol_keep = l2_evict_last();  // the reduce kernel reads these next: keep them in L2 under the activation stream
     if (my_chunks > 0) {
       mbar_wait(acc_done, 0, 22);
       tc_fence_after();
@@ -683,8 +686,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          out[(int64_t)(c * 4 + i) * 256 + m] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          st_hint(&out[(int64_t)(c * 4 + i) * 256 + m],
+                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
+                  pol_keep);
       }
     }
   }
@@ -756,6 +760,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams p, float* __restrict__ grad, const FusedOpt f) {
   griddep_launch();
   griddep_wait();
+  const uint64_t pol_keep = l2_evict_last();  // partials and gradients: small, reused every step, latency-critical
   double sq0 = 0.0, sq1 = 0.0;
   int64_t my_dst = -1;  // FUSED: arena index, value and optimiser segment of this thread's entry
   float my_g = 0.f;
@@ -783,24 +788,24 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
       int k = 0;
       for (; k + 8 <= g.n_part; k += 8) {
         const float* q = src + (int64_t)k * S;
-        const float v0 = __ldcg(q), v1 = __ldcg(q + S), v2 = __ldcg(q + 2 * S), v3 = __ldcg(q + 3 * S);
-        const float v4 = __ldcg(q + 4 * S), v5 = __ldcg(q + 5 * S), v6 = __ldcg(q + 6 * S), v7 = __ldcg(q + 7 * S);
+        const float v0 = ld_hint(q, pol_keep), v1 = ld_hint(q + S, pol_keep), v2 = ld_hint(q + 2 * S, pol_keep), v3 = ld_hint(q + 3 * S, pol_keep);
+        const float v4 = ld_hint(q + 4 * S, pol_keep), v5 = ld_hint(q + 5 * S, pol_keep), v6 = ld_hint(q + 6 * S, pol_keep), v7 = ld_hint(q + 7 * S, pol_keep);
         a0 += v0, a1 += v1, a2 += v2, a3 += v3;
         a0 += v4, a1 += v5, a2 += v6, a3 += v7;
       }
       if (k < g.n_part) {  // up to 7 left: one more batch of independent (predicated) loads
         const float* q = src + (int64_t)k * S;
         const int n = g.n_part - k;
-        const float v0 = __ldcg(q), v1 = n > 1 ? __ldcg(q + S) : 0.f, v2 = n > 2 ? __ldcg(q + 2 * S) : 0.f;
-        const float v3 = n > 3 ? __ldcg(q + 3 * S) : 0.f, v4 = n > 4 ? __ldcg(q + 4 * S) : 0.f, v5 = n > 5 ? __ldcg(q + 5 * S) : 0.f;
-        const float v6 = n > 6 ? __ldcg(q + 6 * S) : 0.f;
+        const float v0 = ld_hint(q, pol_keep), v1 = n > 1 ? ld_hint(q + S, pol_keep) : 0.f, v2 = n > 2 ? ld_hint(q + 2 * S, pol_keep) : 0.f;
+        const float v3 = n > 3 ? ld_hint(q + 3 * S, pol_keep) : 0.f, v4 = n > 4 ? ld_hint(q + 4 * S, pol_keep) : 0.f, v5 = n > 5 ? ld_hint(q + 5 * S, pol_keep) : 0.f;
+        const float v6 = n > 6 ? ld_hint(q + 6 * S, pol_keep) : 0.f;
         a0 += v0, a1 += v1, a2 += v2, a3 += v3;
         a0 += v4, a1 += v5, a2 += v6;
       }
       float* dst = grad + g.dst_off + (g.transpose ? (int64_t)c * g.dst_ld + r : (int64_t)r * g.dst_ld + c);
       float o = p.weight * ((a0 + a1) + (a2 + a3));
       if (!p.overwrite) o += *dst;
-      *dst = o;
+      st_hint(dst, o, pol_keep);
       if (g.net) sq1 += (double)o * o;
       else sq0 += (double)o * o;
       if (FUSED) my_dst = dst - grad, my_g = o, my_net = g.net;
