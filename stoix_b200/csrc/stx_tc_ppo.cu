@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
   // gather and loss-input rows, then the W2 / bias staging below; all of them are in flight together.
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(w_full, 32768 + 131072);
-    for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0);
-    for (int j = 0; j < 4; ++j) tma_load_2d(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0);
+    const uint64_t pol_keep = l2_evict_last();  // the bf16 weights (K4's output) stay L2-resident for all 148 CTAs and the next step
+    for (int j = 0; j < 4; ++j) tma_load_2d_hint(smem + kOffW0 + j * 8192, tmW0, w_full, j * 64, 0, pol_keep);
+    for (int j = 0; j < 4; ++j) tma_load_2d_hint(smem + kOffW1 + j * 32768, tmW1, w_full, j * 64, 0, pol_keep);
   }
   int32_t idx_first = 0;  // producers: row of tile 0 owned by this thread; epilogue (sub 0): its loss-input row of tile 0
   if (p.idx != nullptr && my_tiles > 0) {
@@ -541,8 +542,9 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
   // ---- teardown: bias-gradient and metric partials of this CTA ----
   tc_fence_before();
   __syncthreads();
+  const uint64_t pol_keep = l2_evict_last();  // read by the reduce kernel after K3b has streamed ~140 MB through L2
   for (int i = threadIdx.x; i < 528; i += fb_threads(NEPI))
-    net.db_part[(int64_t)cta_in_net * 528 + i] = (s_db[i] + s_db[528 + i]) + (s_db[2 * 528 + i] + s_db[3 * 528 + i]);
+    st_hint(&net.db_part[(int64_t)cta_in_net * 528 + i], (s_db[i] + s_db[528 + i]) + (s_db[2 * 528 + i] + s_db[3 * 528 + i]), pol_keep);
   {
     __shared__ float s_mw[fb_threads(NEPI) / 32][6];
 #pragma unroll
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
       float acc = 0.f;
       if (threadIdx.x < 6)
         for (int w = 0; w < fb_threads(NEPI) / 32; ++w) acc += s_mw[w][threadIdx.x];
-      p.metric_part[(int64_t)blockIdx.x * 8 + threadIdx.x] = acc;
+      st_hint(&p.metric_part[(int64_t)blockIdx.x * 8 + threadIdx.x], acc, pol_keep);
     }
   }
   if (warp == kFbMmaWarp) {
