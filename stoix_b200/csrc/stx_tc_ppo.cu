@@ -530,8 +530,10 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_hint(tiled_ptr(dout, mrow, c * 4 + j, 32), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]), pol_stream);
-          const float cs = warp_colsum32(dv, lane);
-          dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
+          if (layer == 1) {  // db1; db0 = column sums of dh1 comes out of K3b's dW0 job for free (ones-operand MMA)
+            const float cs = warp_colsum32(dv, lane);
+            dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
+          }
         }
         if (warp == 5) STX_STAMP(26 + (1 - layer));
         STX_STAMP_AT(32 + 4 * it + 2 + (1 - layer), warp == 5 && lane == 0 && it < 4);  // E3 / E4 end of tile it
@@ -571,7 +573,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
 constexpr int kDwThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kDwStages = 3;
 constexpr uint32_t kDwStageBytes = 65536;  // A [64 x 256] 32 KB + B [64 x <=256] 32 KB
-constexpr uint32_t kDwOffBar = kDwStages * kDwStageBytes;
+constexpr uint32_t kDwOffOnes = kDwStages * kDwStageBytes;  // 2 KB: B tile [2 column groups][64 rows][16 B] of bf16 1.0
+constexpr uint32_t kDwOffBar = kDwOffOnes + 2048;
 constexpr uint32_t kDwSmemBytes = kDwOffBar + 128 + 1024;
 constexpr int kMaxJobs = 6;
 
@@ -581,6 +584,8 @@ struct DwJob {
   int cta_begin;   // first CTA of this job
   int n_cta;
   int num_chunks;  // mb / 64
+  float* colsum;   // nullable: [n_cta][256] per-CTA sums over the rows of every A column (A^T * 1): the bias gradient that
+                   // belongs to A = dh1, obtained from one extra N=16 MMA per K step against an all-ones B tile
 };
 struct DwParams {
   DwJob job[kMaxJobs];
@@ -622,6 +627,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
   }
   griddep_launch();
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (job.colsum != nullptr) {  // all-ones B operand (every layout of a constant tile is the same tile)
+    for (int i = threadIdx.x; i < 512; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + kDwOffOnes)[i] = 0x3F803F80u;
+    fence_async_proxy();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -646,6 +655,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_bf16(128, job.N, 1, 1);  // both operands MN-major
+    constexpr uint32_t idesc_ones = idesc_bf16(128, 16, 1, 1);
+    const bool colsum = job.colsum != nullptr;
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % kDwStages;
       mbar_wait(&full[s], (it / kDwStages) & 1, 21);
@@ -658,6 +669,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
           for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128) = column groups 16 h ..
             mma_ss(tmem + h * 256, smem_desc(a0 + h * 16384 + k * 256, 128, 1024, SWIZZLE_NONE),
                    smem_desc(b0 + k * 256, 128, 1024, SWIZZLE_NONE), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (colsum) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)  // columns [N, N+16) of each half: A^T * ones (every column holds the same sums)
+              mma_ss(tmem + h * 256 + job.N, smem_desc(a0 + h * 16384 + k * 256, 128, 1024, SWIZZLE_NONE),
+                     smem_desc(sbase + kDwOffOnes, 128, 1024, SWIZZLE_NONE), idesc_ones, (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty[s]);
       }
@@ -691,6 +708,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
           st_hint(&out[(int64_t)(c * 4 + i) * 256 + m],
                   make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
                   pol_keep);
+      }
+      if (job.colsum != nullptr) {
+        uint32_t r[16];
+        r[0] = 0u;
+        if (my_chunks > 0) {
+          tmem_ld16(tmem + lane_addr + h * 256 + job.N, r);
+          tmem_ld_wait();
+        }
+        st_hint(&job.colsum[(int64_t)cta * 256 + m], __uint_as_float(r[0]), pol_keep);
       }
     }
   }
@@ -899,7 +925,7 @@ inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct TcWs {
   __nv_bfloat16 *h1[2], *h2[2], *dh1[2], *dh2[2], *dz[2], *xg;
-  float *part_w1[2], *part_w2[2], *part_w0[2], *db_part[2], *metric_part;
+  float *part_w1[2], *part_w2[2], *part_w0[2], *db_part[2], *db0_part[2], *metric_part;
   size_t bytes;
 };
 
@@ -924,6 +950,7 @@ TcWs carve_tc(int64_t mb, char* base) {
     w.part_w2[n] = (float*)take((size_t)kDwCtaW2 * 256 * 16 * 4);
     w.part_w0[n] = (float*)take((size_t)kDwCtaW0 * 256 * 64 * 4);
     w.db_part[n] = (float*)take((size_t)kCtaPerNet * 528 * 4);
+    w.db0_part[n] = (float*)take((size_t)kDwCtaW0 * 256 * 4);
   }
   w.xg = (__nv_bfloat16*)take((size_t)mb * 64 * 2);
   w.metric_part = (float*)take((size_t)kNumSMs * 8 * 4);
@@ -1005,17 +1032,17 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     // dW1 = h1^T dh2
     if (int rc = make_map_tiled(&maps.a[jn], ws.h1[n], tiles, 32)) return rc;
     if (int rc = make_map_tiled(&maps.b[jn], ws.dh2[n], tiles, 32)) return rc;
-    dp.job[jn] = DwJob{ws.part_w1[n], 256, cta, kDwCtaW1, chunks};
+    dp.job[jn] = DwJob{ws.part_w1[n], 256, cta, kDwCtaW1, chunks, nullptr};
     cta += kDwCtaW1, ++jn;
     // dW2 = h2^T dz
     if (int rc = make_map_tiled(&maps.a[jn], ws.h2[n], tiles, 32)) return rc;
     if (int rc = make_map_tiled(&maps.b[jn], ws.dz[n], tiles, 2)) return rc;
-    dp.job[jn] = DwJob{ws.part_w2[n], 16, cta, kDwCtaW2, chunks};
+    dp.job[jn] = DwJob{ws.part_w2[n], 16, cta, kDwCtaW2, chunks, nullptr};
     cta += kDwCtaW2, ++jn;
     // dW0^T = dh1^T x
     if (int rc = make_map_tiled(&maps.a[jn], ws.dh1[n], tiles, 32)) return rc;
     if (int rc = make_map_tiled(&maps.b[jn], ws.xg, tiles, 8)) return rc;
-    dp.job[jn] = DwJob{ws.part_w0[n], 64, cta, kDwCtaW0, chunks};
+    dp.job[jn] = DwJob{ws.part_w0[n], 64, cta, kDwCtaW0, chunks, ws.db0_part[n]};  // + db0 = dh1^T * 1
     cta += kDwCtaW0, ++jn;
   }
   dp.n_jobs = jn;
@@ -1042,7 +1069,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     add_seg(ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, kH, o_w1, n, 1);           // dW1[in][out]
     add_seg(ws.part_w0[n], 256 * 64, kDwCtaW0, kH, D, 64, 1, kH, o_w0, n, 1);          // part(j, d) -> W0[d][j]
     add_seg(ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, A, o_w2, n, 1);           // dW2[j][a]
-    add_seg(ws.db_part[n], 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b0, n, 0);
+    add_seg(ws.db0_part[n], 256, kDwCtaW0, 1, kH, 256, 0, kH, o_b0, n, 0);             // db0 from K3b (column sums of dh1)
     add_seg(ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b1, n, 0);
     add_seg(ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, A, o_b2, n, 0);
   }
