@@ -386,6 +386,20 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     // loads below never wait on the index (two chained DRAM latencies would otherwise open every tile)
     // (kept RAW: a conversion right behind the load would stall this in-order warp for the full memory latency)
     int32_t idx_next = idx_first;  // (tile 0: requested in the prologue)
+    // Deferred activation stores.  The SM's global-store path moves 32 B/clk (tools/store_bw.cu): the 2 KB a warp
+    // produces per chunk occupy it for 64 cycles, and all 8 warps finish a chunk at about the same time.  Issued in one
+    // burst, the later stores of a warp block it behind the other warps' bursts; so the four 512-byte stores of a chunk
+    // are issued one at a time between the four column groups of the NEXT chunk this warp processes (whatever phase
+    // that chunk belongs to), where the store path has long drained.
+    uint32_t pend[16];
+    uint4* pend_ptr = nullptr;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pend[j] = 0u;
+#define STX_FLUSH_PENDING(g)                                                                                           \
+  do {                                                                                                                 \
+    if (pend_ptr != nullptr)                                                                                           \
+      st_hint(pend_ptr + (g) * 128, make_uint4(pend[4 * (g)], pend[4 * (g) + 1], pend[4 * (g) + 2], pend[4 * (g) + 3]), pol_stream); \
+  } while (0)
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
@@ -416,10 +430,14 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
-            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
-            pk[j] = pack_bf16(v0, v1);
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int j = 4 * g; j < 4 * g + 4; ++j) {
+              const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
+              const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
+              pk[j] = pack_bf16(v0, v1);
+            }
+            STX_FLUSH_PENDING(g);  // one 512-byte store of the previous chunk (32 lanes = 32 consecutive rows)
           }
           tmem_st16(ta + c * 16, pk);
           tmem_st_wait();
@@ -427,8 +445,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // 32 lanes = 32 consecutive rows -> 512 contiguous bytes per store
-            st_hint(tiled_ptr(hout, mrow, c * 4 + j, 32), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]), pol_stream);
+          for (int j = 0; j < 16; ++j) pend[j] = pk[j];
+          pend_ptr = tiled_ptr(hout, mrow, c * 4, 32);
         }
       }
       // ---------------- E2: head + loss + d(head) ----------------
@@ -513,12 +531,16 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           tmem_ld_wait();
           float dv[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // h is post-relu (>= 0): positive <=> bf16 bit pattern non-zero (and not -0)
-            const bool p0 = (hm[j] & 0x7FFFu) != 0u, p1 = (hm[j] & 0x7FFF0000u) != 0u;
-            dv[2 * j] = p0 ? __uint_as_float(r[2 * j]) : 0.f;
-            dv[2 * j + 1] = p1 ? __uint_as_float(r[2 * j + 1]) : 0.f;
-            pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int j = 4 * g; j < 4 * g + 4; ++j) {
+              // h is post-relu (>= 0): positive <=> bf16 bit pattern non-zero (and not -0)
+              const bool p0 = (hm[j] & 0x7FFFu) != 0u, p1 = (hm[j] & 0x7FFF0000u) != 0u;
+              dv[2 * j] = p0 ? __uint_as_float(r[2 * j]) : 0.f;
+              dv[2 * j + 1] = p1 ? __uint_as_float(r[2 * j + 1]) : 0.f;
+              pk[j] = pack_bf16(dv[2 * j], dv[2 * j + 1]);
+            }
+            STX_FLUSH_PENDING(g);
           }
           if (layer == 1) {  // dh2 replaces h2 as the A operand of G4
             tmem_st16(ta + c * 16, pk);
@@ -528,8 +550,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_hint(tiled_ptr(dout, mrow, c * 4 + j, 32), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]), pol_stream);
+          for (int j = 0; j < 16; ++j) pend[j] = pk[j];
+          pend_ptr = tiled_ptr(dout, mrow, c * 4, 32);
           if (layer == 1) {  // db1; db0 = column sums of dh1 comes out of K3b's dW0 job for free (ones-operand MMA)
             const float cs = warp_colsum32(dv, lane);
             dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
@@ -539,6 +561,9 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
         STX_STAMP_AT(32 + 4 * it + 2 + (1 - layer), warp == 5 && lane == 0 && it < 4);  // E3 / E4 end of tile it
       }
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) STX_FLUSH_PENDING(g);  // the last chunk of the last tile
+#undef STX_FLUSH_PENDING
     STX_STAMP_AT(61, warp == 5 && lane == 0);
   }
   // ---- teardown: bias-gradient and metric partials of this CTA ----

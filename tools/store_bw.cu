@@ -62,23 +62,23 @@ int main() {
   cudaMalloc(&gbuf, 148 * big);
   cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
   const int iters = 4000;
+  for (int grid : {148, 74, 32, 8})
   for (size_t cta_bytes : {(size_t)65536, big})
-    for (int mode = 0; mode < 3; ++mode)
-      for (int warps : {8, 16}) {
-        if (mode == 1 && warps != 8) continue;
+    for (int mode = 0; mode < 2; ++mode)
+      for (int warps : {8}) {
+        if (grid != 148 && mode == 1) continue;
         for (int rep = 0; rep < 2; ++rep) {
-          if (mode == 0) k<0><<<148, warps * 32>>>(iters, cta_bytes, gbuf, out);
-          if (mode == 1) k<1><<<148, warps * 32, 32768>>>(iters, cta_bytes, gbuf, out);
-          if (mode == 2) k<2><<<148, warps * 32>>>(iters, cta_bytes, gbuf, out);
+          if (mode == 0) k<0><<<grid, warps * 32>>>(iters, cta_bytes, gbuf, out);
+          if (mode == 1) k<1><<<grid, warps * 32, 32768>>>(iters, cta_bytes, gbuf, out);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         }
         long long h[148];
         cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
         long long mx = 0;
-        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+        for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
         const double bytes = mode == 1 ? (double)iters * 16384.0 : (double)warps * iters * 2048.0;
-        printf("footprint/CTA %7zu KB mode %d warps %2d: %.1f B/clk/SM (CTA 0), %.1f (slowest CTA)\n", cta_bytes >> 10, mode, warps, bytes / h[0], bytes / mx);
+        printf("grid %3d footprint/CTA %7zu KB mode %d warps %2d: %.1f B/clk/SM (CTA 0), %.1f (slowest CTA)\n", grid, cta_bytes >> 10, mode, warps, bytes / h[0], bytes / mx);
       }
   return 0;
 }
