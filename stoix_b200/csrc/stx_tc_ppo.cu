@@ -284,58 +284,69 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     // Every 256-wide GEMM is issued as four N=64 column parts.  Part p of the NEXT GEMM only needs (a) D part p
     // consumed by the running epilogue and (b) the K-chunks of its A operand written, both announced per part
     // through chunk_done[]; so the tensor pipe trails the epilogue part by part instead of waiting for all of it.
+    // Code shape: groups of four K steps are unrolled (the issuing thread must stay ahead of the 33 cycles an N=64 MMA
+    // takes), the loops over parts and groups are rolled and the descriptors advance by adding byte offsets: fully
+    // unrolled, the ~200 MMA issues of a tile were a third of the kernel's code and the instruction-cache misses at
+    // every phase change stalled the SM for ~2.5k cycles per tile; fully rolled, the issue itself became the bottleneck.
     constexpr uint32_t idesc_fwd = idesc_bf16(128, 64, 0, 1);    // B = W (in,out) image as MN-major
     constexpr uint32_t idesc_head = idesc_bf16(128, 16, 0, 1);
     constexpr uint32_t idesc_bwd = idesc_bf16(128, 64, 0, 0);    // B = same images read as K-major
     constexpr uint32_t idesc_bwd_full = idesc_bf16(128, 256, 0, 0);
     const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
+    auto adv = [](uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); };  // start-address field, no carry (< 256 KB)
+    const uint64_t dW0 = smem_desc(sbase + kOffW0, 8192, 1024, SWIZZLE_128B);
+    const uint64_t dW1f = smem_desc(sbase + kOffW1, 32768, 1024, SWIZZLE_128B);  // forward: MN-major
+    const uint64_t dW1b = smem_desc(sbase + kOffW1, 16, 1024, SWIZZLE_128B);     // backward: K-major
+    const uint64_t dW2f = smem_desc(sbase + kOffW2, 256, 128, SWIZZLE_NONE);
     mbar_wait(w_full, 0, 2);
     STX_STAMP_AT(58, lane == 0);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
       STX_STAMP(0);
       mbar_wait(&x_full[s], (it >> 1) & 1, 3);
-      const uint32_t xa = sbase + kOffX + s * 16384;
-#pragma unroll
+      const uint64_t dX = smem_desc(sbase + kOffX + s * 16384, 16, 1024, SWIZZLE_128B);
+#pragma unroll 1
       for (int pt = 0; pt < 4; ++pt) {  // G0: D = X * W0, trailing E4 of the previous tile
         if (it > 0) mbar_wait(&chunk_done[pt], 1, 4);
         tc_fence_after();
         if (elect_one()) {
+          const uint64_t b0 = adv(dW0, pt * 8192);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_d + pt * 64, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
-                   smem_desc(sbase + kOffW0 + pt * 8192 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_d + pt * 64, adv(dX, k * 32), adv(b0, k * 2048), idesc_fwd, k > 0);
           mma_commit(&d_ready[pt]);
           if (pt == 3) mma_commit(&x_empty[s]);
         }
         __syncwarp();
       }
       STX_STAMP(1);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // G1: D = h1 * W1, trailing E0
         mbar_wait(&chunk_done[j], 0, 5);
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
+#pragma unroll 1
           for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll 1
+            for (int g = (pt == j ? 0 : j); g <= j; ++g) {  // K steps 4g .. 4g+3
+              const uint64_t b0 = adv(dW1f, pt * 32768 + g * 8192);
+              const uint32_t a0 = tmem_a1 + g * 32;
 #pragma unroll
-            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
-              mma_ts(tmem_d + pt * 64, tmem_a1 + k * 8,
-                     smem_desc(sbase + kOffW1 + pt * 32768 + k * 2048, 32768, 1024, SWIZZLE_128B), idesc_fwd, k > 0);
+              for (int kk = 0; kk < 4; ++kk) mma_ts(tmem_d + pt * 64, a0 + kk * 8, adv(b0, kk * 2048), idesc_fwd, (g | kk) != 0);
+            }
             if (j == 3) mma_commit(&d_ready[pt]);
           }
         }
         __syncwarp();
       }
       STX_STAMP(3);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // G2: D[:, :16] = h2 * W2, trailing E1 (columns 0..15 are free after its first part)
         mbar_wait(&chunk_done[j], 1, 6);
         tc_fence_after();
         if (elect_one()) {
+          const uint64_t b0 = adv(dW2f, j * 2048);
 #pragma unroll
-          for (int k = 4 * j; k < 4 * j + 4; ++k)
-            mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_head, k > 0);
+          for (int kk = 0; kk < 4; ++kk) mma_ts(tmem_d, tmem_a2 + j * 32 + kk * 8, adv(b0, kk * 512), idesc_head, (j | kk) != 0);
           if (j == 3) mma_commit(head_ready);
         }
         __syncwarp();
@@ -351,18 +362,20 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
       }
       __syncwarp();
       STX_STAMP(7);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // G4: D = dh2 * W1^T, trailing E3  (W1 image as K-major SW128: 4 K-blocks of 64)
         mbar_wait(&chunk_done[j], 0, 8);
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
+#pragma unroll 1
           for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll 1
+            for (int g = (pt == j ? 0 : j); g <= j; ++g) {  // K steps 4g .. 4g+3 = the g-th 64-wide K block of the image
+              const uint64_t b0 = adv(dW1b, g * 32768 + pt * 8192);
+              const uint32_t a0 = tmem_a2 + g * 32;
 #pragma unroll
-            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
-              mma_ts(tmem_d + pt * 64, tmem_a2 + k * 8,
-                     smem_desc(sbase + kOffW1 + (k >> 2) * 32768 + pt * 8192 + (k & 3) * 32, 16, 1024, SWIZZLE_128B), idesc_bwd,
-                     k > 0);
+              for (int kk = 0; kk < 4; ++kk) mma_ts(tmem_d + pt * 64, a0 + kk * 8, adv(b0, kk * 32), idesc_bwd, (g | kk) != 0);
+            }
             if (j == 3) mma_commit(&d_ready[pt]);
           }
         }
