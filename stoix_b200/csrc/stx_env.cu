@@ -86,14 +86,24 @@ __global__ void synth_env_step_kernel(int64_t E, int D, uint64_t seed, uint64_t 
   }
 }
 
-// ---- keyed bijection on [0, n): cycle-walking 4-round Feistel over the next power of 4 ------
-__device__ __forceinline__ uint32_t feistel(uint32_t x, int half_bits, uint2 key) {
+// ---- keyed bijection on [0, n): cycle-walking 6-round Feistel over the next power of 4 ------
+// Round function: a 32-bit avalanche mixer (two multiply / xor-shift stages) of (right half + round key); the six
+// round keys come from one Philox draw per thread.  (A Philox block per round made this shuffle a 36 us compute-bound
+// kernel; a shuffle needs a keyed bijection with good diffusion, not a cryptographic round function.)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x21f0aaadu;
+  x ^= x >> 15;
+  x *= 0x735a2d97u;
+  x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ uint32_t feistel(uint32_t x, int half_bits, const uint32_t (&rk)[6]) {
   const uint32_t mask = (1u << half_bits) - 1u;
   uint32_t l = x >> half_bits, r = x & mask;
 #pragma unroll
-  for (int round = 0; round < 4; ++round) {
-    const uint4 f = Philox::rand4(make_uint4(r, (uint32_t)round, 0x5045524du, 0u), key);
-    const uint32_t nl = r, nr = l ^ (f.x & mask);
+  for (int round = 0; round < 6; ++round) {
+    const uint32_t nl = r, nr = l ^ (mix32(r + rk[round]) & mask);
     l = nl, r = nr;
   }
   return (l << half_bits) | r;
@@ -106,9 +116,11 @@ __global__ void permutation_kernel(int32_t* __restrict__ perm, int64_t n, int ha
   const uint64_t sid = stream_base + (dev_counter ? *dev_counter : 0ull);
   const uint64_t k = seed ^ (sid * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull);
   const uint2 key = make_uint2((uint32_t)k, (uint32_t)(k >> 32));
+  const uint4 k0 = Philox::rand4(make_uint4(0u, 0u, 0x5045524du, 0u), key), k1 = Philox::rand4(make_uint4(1u, 0u, 0x5045524du, 0u), key);
+  const uint32_t rk[6] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y};
   uint32_t x = (uint32_t)i;
   do {
-    x = feistel(x, half_bits, key);  // a bijection on [0, 4^half_bits); walk the cycle back into [0, n)
+    x = feistel(x, half_bits, rk);  // a bijection on [0, 4^half_bits); walk the cycle back into [0, n)
   } while (x >= (uint64_t)n);
   perm[i] = (int32_t)x;
 }

@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr uint32_t idesc_n64 = idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t idesc_n16 = idesc_bf16(128, 16, 0, 1);
     const uint32_t tmem_d = tmem, tmem_a1 = tmem + 256, tmem_a2 = tmem + 384;
+    // rolled part/group loops with incremental descriptors (see stx_tc_ppo.cu: code size / instruction cache)
+    auto adv = [](uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); };
+    const uint64_t dW0 = smem_desc(sbase + kOffW0, 8192, 1024, SWIZZLE_128B), dW1 = smem_desc(sbase + kOffW1, 32768, 1024, SWIZZLE_128B);
+    const uint64_t dW2 = smem_desc(sbase + kOffW2, 256, 128, SWIZZLE_NONE);
     mbar_wait(w_full, 0, 2);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % kXStages;
@@ -150,42 +154,44 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (it > 0) mbar_wait(head_done, (it - 1) & 1, 4);  // the previous tile's head has left D columns 0..15
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t xa = sbase + kOffX + s * 16384;
-#pragma unroll
+        const uint64_t dX = smem_desc(sbase + kOffX + s * 16384, 16, 1024, SWIZZLE_128B);
+#pragma unroll 1
         for (int pt = 0; pt < 4; ++pt) {  // layer 0: D0 = X (K-major SW128) * W0 (MN-major SW128), K = 64
+          const uint64_t b0 = adv(dW0, pt * 8192);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_d + pt * 64, smem_desc(xa + k * 32, 16, 1024, SWIZZLE_128B),
-                   smem_desc(sbase + kOffW0 + pt * 8192 + k * 2048, 8192, 1024, SWIZZLE_128B), idesc_n64, k > 0);
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_d + pt * 64, adv(dX, k * 32), adv(b0, k * 2048), idesc_n64, k > 0);
           mma_commit(&d_ready[pt]);
         }
         mma_commit(&x_empty[s]);
       }
       __syncwarp();
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // layer 1: D1 = A1 (TMEM) * W1, K = 256, trailing E0
-        mbar_wait(&chunk_done[j], 0, 5);
+        mbar_wait(&chunk_done[j], 0, 34);
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
+#pragma unroll 1
           for (int pt = 0; pt <= j; ++pt) {
+#pragma unroll 1
+            for (int g = (pt == j ? 0 : j); g <= j; ++g) {  // K steps 4g .. 4g+3
+              const uint64_t b0 = adv(dW1, pt * 32768 + g * 8192);
+              const uint32_t a0 = tmem_a1 + g * 32;
 #pragma unroll
-            for (int k = (pt == j ? 0 : 4 * j); k < 4 * j + 4; ++k)
-              mma_ts(tmem_d + pt * 64, tmem_a1 + k * 8, smem_desc(sbase + kOffW1 + pt * 32768 + k * 2048, 32768, 1024, SWIZZLE_128B),
-                     idesc_n64, k > 0);
+              for (int kk = 0; kk < 4; ++kk) mma_ts(tmem_d + pt * 64, a0 + kk * 8, adv(b0, kk * 2048), idesc_n64, (g | kk) != 0);
+            }
             if (j == 3) mma_commit(&d_ready[pt]);
           }
         }
         __syncwarp();
       }
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // head: D2 = A2 (TMEM) * W2 (un-swizzled core matrices), N = 16, trailing E1
-        mbar_wait(&chunk_done[j], 1, 6);
+        mbar_wait(&chunk_done[j], 1, 35);
         tc_fence_after();
         if (elect_one()) {
+          const uint64_t b0 = adv(dW2, j * 2048);
 #pragma unroll
-          for (int k = 4 * j; k < 4 * j + 4; ++k)
-            mma_ts(tmem_d, tmem_a2 + k * 8, smem_desc(sbase + kOffW2 + k * 512, 256, 128, SWIZZLE_NONE), idesc_n16, k > 0);
+          for (int kk = 0; kk < 4; ++kk) mma_ts(tmem_d, tmem_a2 + j * 32 + kk * 8, adv(b0, kk * 512), idesc_n16, (j | kk) != 0);
           if (j == 3) mma_commit(head_ready);
         }
         __syncwarp();

@@ -21,6 +21,9 @@
 //      (deterministic; also the bias gradients and the six loss metrics).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "stx_common.cuh"
 #include "stx_tc_ptx.cuh"
 
@@ -968,7 +971,20 @@ struct TcWs {
 };
 
 constexpr int kCtaPerNet = kNumSMs / 2;              // 74
-constexpr int kDwCtaW1 = 38, kDwCtaW2 = 18, kDwCtaW0 = 18;  // per net: 74
+// split-K CTAs per job and net (sum = 74), proportional to the bytes each job streams (dW1: h1 + dh2, dW2: h2 + dz,
+// dW0: dh1 + x): K3b is HBM-bound, so the CTAs should finish together.  Tuning switch: STX_DW_SPLIT="w1,w2,w0".
+struct DwSplit {
+  int w1 = 35, w2 = 18, w0 = 21;
+  DwSplit() {
+    const char* e = getenv("STX_DW_SPLIT");
+    int a, b, c;
+    if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0 && a + b + c == kCtaPerNet) w1 = a, w2 = b, w0 = c;
+  }
+};
+static const DwSplit g_dw_split;
+#define kDwCtaW1 (g_dw_split.w1)
+#define kDwCtaW2 (g_dw_split.w2)
+#define kDwCtaW0 (g_dw_split.w0)
 
 TcWs carve_tc(int64_t mb, char* base) {
   TcWs w{};

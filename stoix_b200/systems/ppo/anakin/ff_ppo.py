@@ -86,7 +86,7 @@ class _Shard:
         self.advantages = z(T, E)
         self.targets = z(T, E)
         self.logits = z(E, A)
-        self.perm = z(T * E, dt=torch.int32)
+        self.perms = None  # (epochs, T*E) int32 shuffles of this update, allocated by the learner
         self.adv_stats: Optional[torch.Tensor] = None
 
     def step_out(self, t: int) -> StepOut:
@@ -165,6 +165,7 @@ def get_learner_fn(
             peers=None,
             roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # categorical call index
             perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # shuffle stream index
+            side_stream=torch.cuda.Stream(device=dev),                # the shuffles run here, underneath the rollout
             graph=None, eager_done=False,
         )
 
@@ -225,9 +226,23 @@ def get_learner_fn(
                 out=(sh.advantages, sh.targets),
             )
 
-    def _update_phase(state: OnPolicyLearnerState) -> None:
+    def _shuffle_phase(state: OnPolicyLearnerState) -> None:
+        """SHUFFLE MINIBATCHES (ff_ppo.py:294-307) for ALL epochs of this update: one keyed permutation of the flat index per
+        (shard, epoch).  They depend on the key and the device-resident stream counter only, not on the rollout, so the
+        update step issues them on a side stream underneath the rollout (which occupies E/128 of the 148 SMs)."""
+        b = built
+        for u in range(U):
+            sh = b["shards"][u]
+            if sh.perms is None:
+                sh.perms = torch.zeros(epochs, T * E, dtype=torch.int32, device=b["dev"])
+            for ep in range(epochs):
+                ops.make_permutation(T * E, state.key[1] + u, ep, dev_counter=b["perm_ctr"], out=sh.perms[ep])
+
+    def _update_phase(state: OnPolicyLearnerState, shuffled: bool = False) -> None:
         """UPDATE EPOCHS (ff_ppo.py:181-338)."""
         b = built
+        if not shuffled:
+            _shuffle_phase(state)
         sa, sc = b["sa"], b["sc"]
         a_tree = state.params.actor_params
         seeds = state.key
@@ -239,10 +254,8 @@ def get_learner_fn(
             batches = []
             for u in range(U):
                 sh = b["shards"][u]
-                # SHUFFLE MINIBATCHES (ff_ppo.py:294-307): one permutation of the flat index per epoch
-                ops.make_permutation(B, seeds[1] + u, ep, dev_counter=b["perm_ctr"], out=sh.perm)
                 batches.append(ops.PpoBatch(sh.obs[:T].view(B, D), sh.action.view(B), sh.log_prob.view(B), sh.value.view(B),
-                                            sh.advantages.view(B), sh.targets.view(B), sh.adv_stats, sh.perm))
+                                            sh.advantages.view(B), sh.targets.view(B), sh.adv_stats, sh.perms[ep]))
             # single shard on a single device: the gradient reduction can hand sum(g^2) straight to the fused
             # optimiser (no separate norm pass / grid barrier); otherwise the all-reduce sits in between.
             prenorm = precision == ops.STX_PREC_BF16 and U == 1 and world == 1
@@ -297,9 +310,15 @@ def get_learner_fn(
     def _update_step(state: OnPolicyLearnerState) -> None:
         """A single update of the network (ff_ppo.py:61-341), in place on the learner state."""
         _carry_in_phase(state)
+        main = torch.cuda.current_stream()
+        side = built["side_stream"]
+        side.wait_stream(main)  # fork (a graph branch when captured)
+        with torch.cuda.stream(side):
+            _shuffle_phase(state)
         _rollout_phase(state)
         _gae_phase(state)
-        _update_phase(state)
+        main.wait_stream(side)  # join
+        _update_phase(state, shuffled=True)
         _advance_phase(state)
 
     def learner_fn(learner_state: OnPolicyLearnerState) -> AnakinExperimentOutput[OnPolicyLearnerState]:

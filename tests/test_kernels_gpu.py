@@ -216,6 +216,13 @@ def test_permutation_is_a_bijection(n):
     if n == 524288:  # crude mixing check: first minibatch should be spread over the whole range
         first = p[: n // 16].float()
         assert abs(first.mean().item() / n - 0.5) < 0.01
+        # diffusion: neighbours land independently (E|U1-U2| = 1/3), no residual correlation with the index
+        d = (p[1:].long() - p[:-1].long()).abs().float().mean().item() / n
+        assert 0.32 < d < 0.345, d
+        idx = torch.arange(n, device=p.device, dtype=torch.float32)
+        corr = torch.corrcoef(torch.stack([idx, p.float()]))[0, 1].item()
+        assert abs(corr) < 0.01, corr
+        assert (p.long() == torch.arange(n, device=p.device)).sum().item() < 10  # ~1 fixed point expected
 
 
 def test_synthetic_env_contract():

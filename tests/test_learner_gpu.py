@@ -119,7 +119,7 @@ def test_update_batch_size_two_averages_shards():
     assert torch.isfinite(out.learner_state.params.actor_params.arena).all()
     assert not torch.equal(p0, out.learner_state.params.actor_params.arena)
     s0, s1 = learn.built["shards"]
-    assert not torch.equal(s0.obs, s1.obs) and not torch.equal(s0.perm, s1.perm)
+    assert not torch.equal(s0.obs, s1.obs) and not torch.equal(s0.perms, s1.perms)
 
 
 def test_cartpole_learns_with_the_fp32_path():
