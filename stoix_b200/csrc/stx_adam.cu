@@ -90,28 +90,21 @@ __global__ void __launch_bounds__(kAdamThreads)
   if (PEER) {
     // ---- phase 0: cross-rank handshake, then all-reduce by direct peer loads into ps.gsum ----
     const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(ps.local_gen) + 1u;
-    if (blockIdx.x == 0) {
-      if ((int)threadIdx.x < ps.world) {
-        const int peer = threadIdx.x;
+    // block 0 announces; EVERY block polls the local signal pad itself (one hop instead of pad -> block 0 -> flag)
+    if ((int)threadIdx.x < ps.world) {
+      const int peer = threadIdx.x;
+      if (blockIdx.x == 0) {
         __threadfence_system();
         st_release_sys(ps.peer_pads[peer] + ps.rank, gen);
-        while (ld_acquire_sys(ps.my_pad + peer) < gen) {
-        }
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        *reinterpret_cast<volatile unsigned int*>(ps.local_ready) = gen;
+      while (ld_acquire_sys(ps.my_pad + peer) < gen) {
       }
-    } else if (threadIdx.x == 0) {
-      while (*reinterpret_cast<volatile unsigned int*>(ps.local_ready) < gen) {
-      }
-      __threadfence();
     }
     __syncthreads();
     for (int s = 0; s < nseg; ++s) {
       const StxAdamSeg seg = s_seg[s];
       const int64_t n4 = seg.count / 4;
+      float ss = 0.f;  // sum of squares of the scaled sum, accumulated in the order of phase 1 (which PEER then skips)
       for (int64_t i = gtid; i < n4; i += gthreads) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < ps.world; ++r) {  // fixed rank order on every rank
@@ -119,20 +112,27 @@ __global__ void __launch_bounds__(kAdamThreads)
           acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
         }
         reinterpret_cast<float4*>(ps.gsum + seg.offset)[i] = acc;
+        float4 g = acc;
+        g.x *= h.grad_scale, g.y *= h.grad_scale, g.z *= h.grad_scale, g.w *= h.grad_scale;
+        ss += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
       }
       for (int64_t i = n4 * 4 + gtid; i < seg.count; i += gthreads) {
         float acc = 0.f;
         for (int r = 0; r < ps.world; ++r) acc += __ldcg(ps.peer_grads[r] + seg.offset + i);
         ps.gsum[seg.offset + i] = acc;
+        const float g = acc * h.grad_scale;
+        ss += g * g;
       }
+      const double bs = block_sum<double>((double)ss, sred);
+      if (threadIdx.x == 0) partials[(int64_t)s * gridDim.x + blockIdx.x] = bs;
     }
-    __syncthreads();  // this block re-reads only what it wrote (same index mapping in the phases below)
+    __syncthreads();  // this block re-reads only what it wrote (same index mapping in phase 2)
     G = ps.gsum;
   }
 
   // ---- phase 1: per-segment sum of squares of (grad * grad_scale) ----
   // (PRENORM: the producer of the gradients already left sum(g^2) partials of the unscaled gradients here)
-  for (int s = 0; s < nseg && !PRENORM; ++s) {
+  for (int s = 0; s < nseg && !PRENORM && !PEER; ++s) {
     const StxAdamSeg seg = s_seg[s];
     const float4* g4 = reinterpret_cast<const float4*>(G + seg.offset);
     const int64_t n4 = seg.count / 4;
