@@ -357,7 +357,7 @@ def run_ours(args):
                     "frac": upd_tflops / peaks["bf16_tflops_sustained"],
                     # dram__bytes_read+write per minibatch launch pair from the committed ncu capture
                     # (profiles/r01_k3_ncu.txt: K3a 96.7 MB + K3b 144.8 MB); null for the fp32 path
-                    "traffic": 2.415e8 if precision == "bf16" else None, "traffic_unit": "bytes per minibatch step (K3a+K3b)",
+                    "traffic": 2.393e8 if precision == "bf16" else None, "traffic_unit": "bytes per minibatch step (K3a+K3b)",
                     "peak_source": f"{peaks['source']} (sustained bf16 cuBLAS)", "flops_per_env_step": upd_f}
         gae_gbs = 22.0 * T * E_PER_GPU / (phase_ms["gae"] * 1e-3) / 1e9
         gae_roof = {"kernel": "K2 gae_scan_kernel", "bound": "hbm", "shape": [T, E_PER_GPU], "achieved": gae_gbs, "peak": peaks["hbm_gbs"],
