@@ -31,8 +31,8 @@ struct AdamScratch {
 
 // ---- C1 fused into K4: one-shot all-reduce over NVLink peer memory ------------------------------------
 // Every rank's gradient arena lives in symmetric (peer-mapped) memory.  Rank r announces "my gradients of
-// call #gen are complete" by writing gen into slot r of every peer's signal pad, waits until all peers
-// announced the same, then each rank sums the W arenas in rank order straight from peer memory (ld.global
+// call #gen are complete" by writing gen into slot r of every peer's signal pad (block 0), every block waits until
+// all peers announced the same (polling the local pad), then each rank sums the W arenas in rank order straight from peer memory (ld.global
 // over NVLink) -- identical association order everywhere => bit-identical parameters on all ranks.  The
 // gradient arenas are ping-ponged by the caller, so this single handshake per call also guarantees that a
 // buffer is not overwritten while a peer may still be reading it.
@@ -41,7 +41,6 @@ struct PeerSync {
   unsigned int* peer_pads[8];   // signal pads of every rank (slot [rank] is written by that rank)
   unsigned int* my_pad;
   unsigned int* local_gen;      // device counter: number of completed calls
-  unsigned int* local_ready;    // released by block 0 once every peer has signalled
   float* gsum;                  // local arena receiving the summed gradient
   int world, rank;
 };
@@ -348,7 +347,6 @@ extern "C" int stx_allreduce_clip_adam_step(float* param_arena, const float* con
   char* sc = reinterpret_cast<char*>(scratch);
   const size_t base = sizeof(AdamScratch) + sizeof(double) * kAdamMaxSegs * kNumSMs;
   ps.local_gen = reinterpret_cast<unsigned int*>(sc + base);
-  ps.local_ready = reinterpret_cast<unsigned int*>(sc + base + 8);
   ps.gsum = gsum, ps.world = world, ps.rank = rank;
   STX_CUDA_OK(launch_pdl(clip_adam_kernel<false, true>, dim3(kNumSMs), dim3(kAdamThreads), 0, (cudaStream_t)stream, param_arena,
                          static_cast<const float*>(gsum), mu, nu, counts, segs, nseg, *hyper,

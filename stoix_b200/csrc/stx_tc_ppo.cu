@@ -9,16 +9,23 @@
 //        G3 dz*W2^T -> E3 dh2 = .*(h2>0) -> G4 dh2*W1^T -> E4 dh1 = .*(h1>0)
 //      All five GEMMs run on tcgen05 with the hidden activations resident in tensor memory (A operand
 //      from TMEM); W1's single smem image serves as MN-major B (forward) and K-major B (backward).
-//      Epilogue warps also emit h1, h2, dh2, dh1, dz (bf16) for the weight-gradient GEMMs, reduce the
-//      bias gradients with a shuffle butterfly and accumulate the loss metrics.
+//      Every 256-wide GEMM is issued as four N=64 column parts with their own mbarriers, so the tensor pipe
+//      trails the epilogue part by part (TMEM is full: two tiles cannot be in flight).
+//      Epilogue warps also emit h1, h2, dh2, dh1, dz (bf16) for the weight-gradient GEMMs -- deferred, one
+//      512-byte store at a time between the column groups of the next chunk, because the SM's store path
+//      (32 B/clk) is this kernel's roofline --, reduce the layer-1 / head bias gradients with a shuffle
+//      butterfly and accumulate the loss metrics.
 //  tc_dw_kernel (K3b)  split-K GEMMs dW = A^T * B over the minibatch rows with both operands MN-major,
 //      3-stage TMA/mbarrier pipeline, 256 x N fp32 accumulators in TMEM:
-//        dW1 = h1^T dh2 (N=256), dW2 = h2^T dz (N=16), dW0^T = dh1^T x (N=64).
+//        dW1 = h1^T dh2 (N=256), dW2 = h2^T dz (N=16), dW0^T = dh1^T x (N=64) + db0 = dh1^T 1 (ones-operand MMA).
 //      The activations travel K3a -> K3b in a tiled layout [tile of 128 rows][8-column group][row][8]:
 //      a warp of K3a (one row per thread) stores 512 contiguous bytes per instruction, and one TMA box of
 //      K3b lands 64 rows of every column group as un-swizzled UMMA core matrices (8 rows x 16 B).
 //  tc_reduce_kernel     fixed-order reduction of the per-CTA partials into the flat fp32 gradient arena
-//      (deterministic; also the bias gradients and the six loss metrics).
+//      (deterministic; also the bias gradients and the six loss metrics); optionally fused with clip + Adam
+//      (stx_ppo_minibatch_update).
+// The three kernels (and K4 behind them) are chained with programmatic dependent launch; activations carry
+// evict_first, partials / gradients evict_last L2 policies (see stx_common.cuh).
 #include <cuda.h>
 
 #include <cstdio>
