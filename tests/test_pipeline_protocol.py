@@ -240,3 +240,124 @@ def test_the_model_catches_broken_protocols(mutation):
     with pytest.raises(AssertionError):
         for seed in range(150):
             run(seed * 104729 + 1, 4, mutation)
+
+
+# ======================================================================================================================
+# The forward-only variant of the same scheme: tc_rollout_kernel (stx_tc_rollout.cu) / tc_mlp_fwd_kernel (stx_tc_mlp.cu).
+# Per step t: G0 (4 parts, after head_done(t-1)) -> E0 -> G1 (trailing) -> E1 -> G2 (head, trailing) -> E2 reads the head.
+# The environment producers run one step ahead: they fill X stage (t+1)&1 during step t (x_empty gate from t >= 1).
+# ======================================================================================================================
+
+
+def ro_producer(m, steps):
+    m.X[0] = ("x", 0)  # stage 0 <- the carried observation
+    m.x_full[0].arrive()
+    yield
+    for t in range(steps):
+        if t + 1 < steps:
+            s = (t + 1) & 1
+            if t >= 1:
+                yield from m.wait("prod", m.x_empty[s], ((t - 1) >> 1) & 1)
+            assert m.X[s] is None or m.X[s][1] == t - 1, f"X stage {s} overwritten while it holds {m.X[s]} (producing step {t + 1})"
+            m.X[s] = ("x", t + 1)
+            yield
+            m.x_full[s].arrive()
+        yield
+
+
+def ro_mma(m, steps):
+    def issue(check, effect):
+        m.pipe.append(lambda: (check(), effect()))
+
+    for t in range(steps):
+        s = t & 1
+        yield from m.wait("mma", m.x_full[s], (t >> 1) & 1)
+        if t > 0:
+            yield from m.wait("mma", m.head_done, (t - 1) & 1)
+        for pt in range(PARTS):
+            def chk(pt=pt, t=t, s=s):
+                assert m.X[s] == ("x", t), f"G0 step {t} reads X stage {s} = {m.X[s]}"
+                assert m.D[pt] is None or m.D[pt] == ("free", t - 1), f"G0 step {t} overwrites D[{pt}] = {m.D[pt]}"
+                assert pt != 0 or t == 0 or m.head == ("read", t - 1), f"G0 step {t} overwrites the head columns: {m.head}"
+            issue(chk, lambda pt=pt, t=t: m.D.__setitem__(pt, ("G0", t)))
+            m.pipe.append(m.d_ready[pt].arrive)
+        m.pipe.append(m.x_empty[s].arrive)
+        yield
+        for j in range(PARTS):  # G1 trailing E0
+            yield from m.wait("mma", m.chunk_done[j], 0)
+            for pt in range(j + 1):
+                for g in (range(0, j + 1) if pt == j else [j]):
+                    def chk(pt=pt, g=g, t=t):
+                        for c in (2 * g, 2 * g + 1):
+                            assert m.A1[c] == ("h1", t), f"G1 step {t} reads h1 chunk {c} = {m.A1[c]}"
+                        if g == 0:
+                            assert m.D[pt] == ("free", t), f"G1 step {t} overwrites D[{pt}] = {m.D[pt]}"
+                    issue(chk, lambda pt=pt, g=g, t=t: m.D.__setitem__(pt, ("busy", "G1", t, g)))
+                if j == 3:
+                    def fin(pt=pt, t=t):
+                        assert m.D[pt] == ("busy", "G1", t, 3)
+                        m.D[pt] = ("G1", t)
+                    m.pipe.append(fin)
+                    m.pipe.append(m.d_ready[pt].arrive)
+            yield
+        for j in range(PARTS):  # head trailing E1
+            yield from m.wait("mma", m.chunk_done[j], 1)
+            def chk(j=j, t=t):
+                for c in (2 * j, 2 * j + 1):
+                    assert m.A2[c] == ("h2", t), f"G2 step {t} reads h2 chunk {c} = {m.A2[c]}"
+                assert m.D[0] == ("free", t), f"G2 step {t} writes the head columns while D[0] = {m.D[0]}"
+            issue(chk, lambda: None)
+            if j == 3:
+                m.pipe.append(lambda t=t: setattr(m, "head", ("G2", t)))
+                m.pipe.append(m.head_ready.arrive)
+            yield
+
+
+def ro_epilogue(m, half, steps):
+    who = f"epi{half}"
+    for t in range(steps):
+        for layer, (gemm, dst, kind, prev_kind) in enumerate((("G0", m.A1, "h1", "h1"), ("G1", m.A2, "h2", "h2"))):
+            for cc in range(PARTS):
+                c = cc * 2 + half
+                yield from m.wait(who, m.d_ready[cc], layer)
+                assert m.D[cc] == (gemm, t), f"E{layer} step {t} reads D[{cc}] = {m.D[cc]}, wants {gemm}"
+                yield
+                assert dst[c] is None or dst[c] == (prev_kind, t - 1), f"E{layer} step {t} overwrites {kind} chunk {c} = {dst[c]}"
+                dst[c] = (kind, t)
+                if m.chunk_done[cc].pending == 1:
+                    m.D[cc] = ("free", t)
+                m.chunk_done[cc].arrive()
+                yield
+        if half == 0:
+            yield from m.wait(who, m.head_ready, t & 1)
+            assert m.head == ("G2", t), f"E2 step {t} reads head = {m.head}"
+            m.head = ("read", t)
+            m.head_done.arrive()
+            yield
+
+
+def run_forward(seed, steps):
+    rng = random.Random(seed)
+    m = Model(steps, rng)
+    actors = {"prod": ro_producer(m, steps), "mma": ro_mma(m, steps), "epi0": ro_epilogue(m, 0, steps), "epi1": ro_epilogue(m, 1, steps)}
+    idle = 0
+    bars = m.d_ready + m.chunk_done + [m.head_ready, m.head_done] + m.x_full + m.x_empty
+    while actors or m.pipe:
+        pick = rng.choice(list(actors) + (["pipe"] if m.pipe else []))
+        before = (tuple(b.phase for b in bars), len(m.pipe))
+        if pick == "pipe":
+            m.pipe_step()
+        else:
+            try:
+                next(actors[pick])
+            except StopIteration:
+                del actors[pick]
+        idle = idle + 1 if before == (tuple(b.phase for b in bars), len(m.pipe)) else 0
+        assert idle < 20000, f"deadlock (seed {seed}): still running {sorted(actors)}, pipe {len(m.pipe)}"
+    assert m.head == ("read", steps - 1)
+
+
+@pytest.mark.parametrize("steps", [1, 2, 5])
+def test_forward_and_rollout_barrier_protocol_under_random_schedules(steps):
+    for seed in range(150):
+        run_forward(seed * 6151 + steps, steps)
