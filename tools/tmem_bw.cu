@@ -34,7 +34,7 @@ __global__ void k(int iters, long long* out, uint32_t* sink, uint4* gbuf) {
     if (MODE == 2) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        gbuf[((size_t)(blockIdx.x * 64 + (i & 63)) * 32 + (warp * 4 + j)) * 32 + lane] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        gbuf[((size_t)(blockIdx.x * 64 + (i & 63)) * 64 + (warp * 4 + j)) * 32 + lane] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     }
   }
   __syncthreads();
@@ -52,7 +52,7 @@ int main() {
   uint4* gbuf;
   cudaMalloc(&out, 148 * 8);
   cudaMalloc(&sink, 4096);
-  cudaMalloc(&gbuf, (size_t)148 * 64 * 32 * 32 * 16);
+  cudaMalloc(&gbuf, (size_t)148 * 64 * 64 * 32 * 16);  // [CTA][iteration & 63][store slot <= 16 warps x 4][lane] x 16 B
   const int iters = 2000;
   for (int mode = 0; mode < 3; ++mode)
     for (int warps : {4, 8, 16}) {
