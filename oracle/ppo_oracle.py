@@ -162,10 +162,11 @@ def init_mlp(rng, sizes: Sequence[int], head_scale: float, dtype=np.float64) -> 
 
 
 def _bf16_round(x: np.ndarray) -> np.ndarray:
-    """Round-to-nearest-even to bfloat16 precision (emulates the tcgen05 operand format)."""
+    """Round-to-nearest-even to bfloat16 precision (emulates the tcgen05 operand format).
+    uint32 arithmetic throughout (the carry of the rounding add never leaves 32 bits for finite inputs)."""
     x32 = np.ascontiguousarray(x, dtype=np.float32)
-    u = x32.view(np.uint32).astype(np.uint64)
-    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    u = x32.view(np.uint32)
+    rounded = (u + (np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1)))) & np.uint32(0xFFFF0000)
     out = rounded.view(np.float32).reshape(x32.shape)
     return out.astype(x.dtype if x.dtype in (np.float32, np.float64) else np.float32)
 

@@ -26,7 +26,8 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
 
 
 def u01(x):
-    return ((np.asarray(x, np.uint64) >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    # 23 bits + half-step offset (stx_common.cuh u01): k + 0.5 is exact in fp32, the result is never 0 or 1
+    return ((np.asarray(x, np.uint64) >> np.uint64(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
 
 
 def normal2(a, b):

@@ -117,15 +117,31 @@ def _merge(dst: Dict[str, Any], src: Dict[str, Any]) -> Dict[str, Any]:
     return dst
 
 
+class _Loader(yaml.SafeLoader):
+    """SafeLoader whose float resolver also accepts exponents without a dot (`3e-4`, `1e7`): PyYAML follows YAML 1.1
+    and reads those as strings, OmegaConf (the reference's loader) as floats."""
+
+
+_Loader.add_implicit_resolver(
+    "tag:yaml.org,2002:float",
+    re.compile(r"""^(?:[-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?
+                    |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
+                    |\.[0-9][0-9_]*(?:[eE][-+]?[0-9]+)?
+                    |[-+]?\.(?:inf|Inf|INF)
+                    |\.(?:nan|NaN|NAN))$""", re.X),
+    list("-+0123456789."),
+)
+
+
 def _load_yaml(path: Path) -> Dict[str, Any]:
     if not path.exists():
         raise FileNotFoundError(f"config file not found: {path}")
-    return yaml.safe_load(path.read_text()) or {}
+    return yaml.load(path.read_text(), Loader=_Loader) or {}
 
 
 def _parse_value(text: str) -> Any:
     try:
-        return yaml.safe_load(text)
+        return yaml.load(text, Loader=_Loader)
     except yaml.YAMLError:
         return text
 

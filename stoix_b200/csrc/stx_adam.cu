@@ -60,8 +60,9 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* arrive) {
     __threadfence();
     const unsigned long long t = atomicAdd(arrive, 1ull);
     const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
-    while (*reinterpret_cast<volatile unsigned long long*>(arrive) < target) {
-    }
+    unsigned int spins = 0;
+    unsigned long long t0 = 0ull;
+    while (*reinterpret_cast<volatile unsigned long long*>(arrive) < target) spin_guard(spins, t0, "optimiser grid barrier");
     __threadfence();
   }
   __syncthreads();
@@ -96,8 +97,9 @@ __global__ void __launch_bounds__(kAdamThreads)
         __threadfence_system();
         st_release_sys(ps.peer_pads[peer] + ps.rank, gen);
       }
-      while (ld_acquire_sys(ps.my_pad + peer) < gen) {
-      }
+      unsigned int spins = 0;
+      unsigned long long t0 = 0ull;
+      while (ld_acquire_sys(ps.my_pad + peer) < gen) spin_guard(spins, t0, "peer gradient hand-shake");
     }
     __syncthreads();
     for (int s = 0; s < nseg; ++s) {

@@ -138,8 +138,10 @@ struct Philox {
   }
 };
 
-// uniform in (0,1): never 0 or 1 (24-bit mantissa + half-ulp offset)
-__host__ __device__ static inline float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1): never 0 or 1.  23 random bits + half-step offset: k + 0.5 is exact in fp32 for every k < 2^23
+// (with 24 bits the odd k >= 2^23 round half-to-even and k = 2^24 - 1 yields exactly 1.0, i.e. -log(-log(u)) = +inf
+// in the Gumbel-max sampler).
+__host__ __device__ static inline float u01(uint32_t x) { return ((x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 #ifdef __CUDACC__
 // two N(0,1) from two words (Box-Muller, full-precision log/sincos: this is a synthetic data source
@@ -149,6 +151,19 @@ __device__ static inline float2 normal2(uint32_t a, uint32_t b) {
   float s, c;
   sincospif(2.0f * u01(b), &s, &c);
   return make_float2(r * c, r * s);
+}
+
+// Bounded spin for cross-block / cross-GPU flag waits: a protocol error traps (with a message) after ~4 s instead of
+// hanging the GPU.  `spins` is the caller's loop counter; the wall clock is only consulted every 1024 polls.
+__device__ __forceinline__ void spin_guard(unsigned int& spins, unsigned long long& t0, const char* what) {
+  if ((++spins & 1023u) != 0u) return;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0ull) t0 = now;
+  else if (now - t0 > 4000000000ull) {
+    printf("[stx] spin-wait timeout (%s): block %d thread %d\n", what, blockIdx.x, threadIdx.x);
+    __trap();
+  }
 }
 
 // ---- deterministic block reductions ---------------------------------------------------------

@@ -23,7 +23,26 @@ class CartPoleEnv(Environment):
 
     def __init__(self, device="cuda", seed: int = 0):
         self.device = torch.device(device)
-        self.seed = int(seed)  # reset states come from torch's default CUDA generator (CUDA-graph safe)
+        self._seed = int(seed)
+        self._gen = None  # dedicated generator: reset states are a function of the seed, not of torch's global stream
+
+    @property
+    def seed(self) -> int:
+        return self._seed
+
+    @seed.setter
+    def seed(self, value: int) -> None:
+        """learner_setup assigns `arch.seed + 7919 * rank + ...` per rank / shard (the reference splits its reset
+        keys per device, batch and env, ff_ppo.py:492-501): re-seeding restarts the reset-state stream."""
+        self._seed = int(value)
+        if self._gen is not None:
+            self._gen.manual_seed(self._seed)
+
+    def _generator(self) -> torch.Generator:
+        if self._gen is None:
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(self._seed)
+        return self._gen
 
     def observation_space(self) -> ArraySpace:
         return ArraySpace((4,), torch.float32, self.device)
@@ -32,7 +51,7 @@ class CartPoleEnv(Environment):
         return DiscreteSpace(2)
 
     def _fresh(self, E: int) -> torch.Tensor:
-        return (torch.rand(E, 4, device=self.device) - 0.5) * 0.1
+        return (torch.rand(E, 4, device=self.device, generator=self._generator()) - 0.5) * 0.1
 
     def reset(self, keys) -> Tuple[Dict[str, Any], TimeStep]:
         E, dev = len(keys), self.device

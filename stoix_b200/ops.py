@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import STX_PREC_BF16, STX_PREC_F32, StxError
 
 _scratch: Dict[Tuple, torch.Tensor] = {}
+_retired: List[torch.Tensor] = []  # outgrown scratch tensors: a captured CUDA graph may still hold their raw pointers
 
 
 def _need_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
@@ -40,10 +41,17 @@ def _stream():
 
 
 def _zeros_scratch(key: Tuple, nbytes: int, device) -> torch.Tensor:
-    """Zero-initialised scratch that persists (kernels restore their counters after use)."""
+    """Zero-initialised scratch that persists (kernels restore their counters after use).
+
+    A scratch that has been handed out is NEVER returned to the allocator: a captured update-step graph holds
+    its raw pointer, so when a later (larger) request outgrows it the old tensor is retired, not freed --
+    replays keep writing into memory nobody else owns.  Callers with their own life cycle (learner, evaluator)
+    pass distinct keys so that they do not share workspaces in the first place."""
     full = key + (str(device),)
     t = _scratch.get(full)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _retired.append(t)
         t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _scratch[full] = t
     return t
@@ -154,7 +162,7 @@ def gae_generic(r_t, discount_t, lambda_, v_tm1, v_t, truncation_t=None, standar
 
 def mlp_forward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, row_idx: Optional[torch.Tensor] = None,
                 precision: int = STX_PREC_F32, params_bf16: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, ws_key: str = "fwd") -> torch.Tensor:
     dev = _need_cuda(params, x, row_idx, params_bf16)
     want = torch.float32 if precision == STX_PREC_F32 else torch.bfloat16
     if x.dtype != want or x.ndim != 2 or x.shape[1] != spec.sizes[0]:
@@ -167,7 +175,7 @@ def mlp_forward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, row_idx: O
     if out is None:
         out = torch.empty((M, spec.sizes[-1]), dtype=torch.float32, device=dev)
     nbytes = lib.stx_mlp_forward_workspace_bytes(C.byref(m), M, precision)
-    ws = _zeros_scratch(("fwd", precision), nbytes, dev)
+    ws = _zeros_scratch((ws_key, precision), nbytes, dev)
     _lib.check(
         lib.stx_mlp_forward(C.byref(m), _p(x), x.stride(0), _p(row_idx), M, _p(out), precision, _p(ws),
                             ws.numel(), _stream()),

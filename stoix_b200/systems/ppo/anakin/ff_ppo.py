@@ -175,7 +175,7 @@ def get_learner_fn(
         sh: _Shard = b["shards"][u]
         a_tree = state.params.actor_params
         # SELECT ACTION (ff_ppo.py:97-101): logits -> sample -> log_prob
-        ops.mlp_forward(b["sa"], a_tree.flat, sh.obs[t], precision=precision, params_bf16=a_tree.flat_bf16, out=sh.logits)
+        ops.mlp_forward(b["sa"], a_tree.flat, sh.obs[t], precision=precision, params_bf16=a_tree.flat_bf16, out=sh.logits, ws_key="learner")
         ops.categorical(sh.logits, None, seeds[0] + u, t, b["roll_ctr"], out=(sh.action[t], sh.log_prob[t]))
         # STEP ENVIRONMENT (ff_ppo.py:104-116)
         if has_step_into:
@@ -212,9 +212,9 @@ def get_learner_fn(
                     _env_step(state, u, t, state.key)
             # value = critic(obs_t), bootstrap_value = critic(next_obs_t) (ff_ppo.py:99,113-116), batched
             ops.mlp_forward(sc, c_tree.flat, sh.obs[:T].view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
-                            out=sh.value.view(B, 1))
+                            out=sh.value.view(B, 1), ws_key="learner")
             ops.mlp_forward(sc, c_tree.flat, sh.next_obs.view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
-                            out=sh.bootstrap_value.view(B, 1))
+                            out=sh.bootstrap_value.view(B, 1), ws_key="learner")
 
     def _gae_phase(state: OnPolicyLearnerState) -> None:
         """CALCULATE ADVANTAGE (ff_ppo.py:164-179)."""

@@ -19,9 +19,17 @@ class Checkpointer:
         self.dir = Path.cwd() / rel_dir / model_name / uid
         self.metadata = metadata or {}
         self.max_to_keep = max_to_keep
+        self.save_interval_steps = max(int(save_interval_steps), 1)
+        if keep_period is not None:
+            raise NotImplementedError("Checkpointer(keep_period=...) is not supported by the torch.save store")
         self.best = -float("inf")
+        self._last_saved: Optional[int] = None
 
     def save(self, timestep: int, unreplicated_learner_state, episode_return: float = 0.0) -> bool:
+        """checkpointing.py:88-127: a step is written when it is at least save_interval_steps past the last one."""
+        if self._last_saved is not None and int(timestep) - self._last_saved < self.save_interval_steps:
+            return False
+        self._last_saved = int(timestep)
         self.dir.mkdir(parents=True, exist_ok=True)
         p = unreplicated_learner_state.params.actor_params
         blob = {"timestep": int(timestep), "episode_return": float(episode_return), "metadata": self.metadata,
@@ -38,7 +46,13 @@ class Checkpointer:
         return True
 
     def restore_params(self, arena: torch.Tensor, timestep: Optional[int] = None) -> torch.Tensor:
-        path = self.dir / (f"{timestep}.pt" if timestep is not None else "best.pt")
+        """checkpointing.py:129-179: restores the requested step, by default the LATEST saved one."""
+        if timestep is None:
+            steps = sorted(int(q.stem) for q in self.dir.glob("*.pt") if q.stem.isdigit())
+            if not steps:
+                raise FileNotFoundError(f"no checkpoint under {self.dir}")
+            timestep = steps[-1]
+        path = self.dir / f"{timestep}.pt"
         blob = torch.load(path, map_location="cpu")
         arena.copy_(blob["params"])
         return arena

@@ -1,10 +1,22 @@
-"""Two-rank data-parallel update (the reference's pmap 'device' axis -> one process per GPU + NCCL
-all-reduce of the flat gradient arena, ff_ppo.py:258-261).  Needs >= 2 GPUs; run with
-`gpurun --gpus 2 -- python -m pytest tests/test_distributed_gpu.py -m gpu`."""
+"""Data-parallel update (the reference's pmap 'device' axis, ff_ppo.py:253-261 -> one process per GPU, mean of ONE flat
+gradient arena per minibatch step) on the GPU, checked against the ORACLE:
+
+* `test_fused_allreduce_kernel_on_one_device` (runs on a 1-GPU box): the fused all-reduce + clip + Adam kernel
+  (`stx_allreduce_clip_adam_step`) driven through the C ABI with W = 2 / 4 / 8 "virtual ranks" whose gradient arenas and
+  signal pads are plain buffers of the same device; every virtual rank's parameters / moments must equal
+  `oracle.clip_adam_step(mean of the W gradients)` and be bit-identical to each other.
+* `test_two_rank_update_matches_oracle` (needs >= 2 GPUs; `gpurun --gpus 2`): two torchrun ranks run three whole update
+  steps (eager, graph capture, graph replay); each rank replays its own trajectory through `oracle.ppo_update` with the
+  gradient exchange as `grad_sync` (a gloo all-reduce between the two oracle instances: SUM, then 1/world) and compares its
+  post-update optimiser state and parameters with the oracle's, for the fused NVLink all-reduce and for NCCL.
+"""
+import ctypes as C
+import json
 import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -12,61 +24,187 @@ pytestmark = pytest.mark.gpu
 
 WORKER = r'''
 import os, sys, json
+import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, os.getcwd())
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-from stoix_b200 import random as srandom
+cpu_group = dist.new_group(backend="gloo")       # carries the ORACLE's gradient exchange (CPU tensors)
+from oracle import ppo_oracle as O
+from stoix_b200 import ops, random as srandom
 from stoix_b200.config import compose
 from stoix_b200.systems.ppo.anakin import ff_ppo
 from stoix_b200.utils import make_env
 from stoix_b200.utils.total_timestep_checker import check_total_timesteps
 precision, fused = sys.argv[1], sys.argv[2]
-E, T = 256, 16
+bf16 = precision == "bf16"
+E, T, nmb, n_upd = 256, 16, 4, 3
 cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E * world}", f"system.rollout_length={T}",
-                                 "system.num_minibatches=4", f"arch.total_timesteps={E * world * T * 4}", "arch.num_evaluation=1",
-                                 f"arch.precision={precision}", f"arch.fused_allreduce={fused}", "logger.use_console=False"])
+                                 f"system.num_minibatches={nmb}", f"arch.total_timesteps={E * world * T * n_upd}", "arch.num_evaluation=1",
+                                 f"arch.precision={precision}", f"arch.fused_allreduce={fused}", "logger.use_console=False",
+                                 "env.kwargs.p_term=0.05", "env.kwargs.p_trunc=0.05"])
 cfg.num_devices, cfg.rank = world, rank
 cfg = check_total_timesteps(cfg, quiet=True)
+assert cfg.arch.num_envs == E and cfg.arch.num_updates == n_upd
 env, _ = make_env.make(cfg)
 keys = srandom.split(srandom.PRNGKey(cfg.arch.seed), 4)
 learn, _, state = ff_ppo.learner_setup(env, (keys[0], keys[2], keys[3]), cfg)
+with torch.no_grad():   # non-trivial biases / heads, identical on every rank
+    g = torch.Generator(device="cuda").manual_seed(1)
+    arena = state.params.actor_params.arena
+    arena.add_(torch.randn(arena.shape, device="cuda", generator=g) * 0.05)
+    if bf16:
+        ops.cast_bf16(arena, out=state.params.actor_params.arena_bf16)
 cfg.arch.num_updates_per_eval = 1
-p0 = state.params.actor_params.arena.clone()
-for _ in range(3):   # eager, capture, replay
+f64 = lambda t: t.detach().float().cpu().numpy().astype(np.float64)
+tree = lambda tr: O.MLPParams.from_flat(f64(tr.flat), list(tr.spec.sizes))
+actor, critic = tree(state.params.actor_params), tree(state.params.critic_params)
+n_a, n_c = actor.flat().size, critic.flat().size
+a_st, c_st = O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c))
+h = O.PPOHyper(num_minibatches=nmb, num_updates=n_upd)
+rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+def grad_sync(a_g, c_g, info):   # pmean over "device": all-reduce SUM of one flat arena, 1/world in the optimiser
+    flat = torch.from_numpy(np.concatenate([a_g, c_g]).astype(np.float64))
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=cpu_group)
+    flat = flat.numpy() * (1.0 / world)
+    m = torch.tensor([info["actor_loss"], info["entropy"], info["value_loss"]], dtype=torch.float64)
+    dist.all_reduce(m, op=dist.ReduceOp.SUM, group=cpu_group)
+    m = m.numpy() / world
+    return flat[: a_g.size], flat[a_g.size:], {**info, "actor_loss": m[0], "entropy": m[1], "value_loss": m[2]}
+
+worst = {"params_abs": 0.0, "moments_rel": 0.0, "metrics_rel": 0.0}
+ok, why = True, ""
+for upd in range(n_upd):   # eager, graph capture, graph replay
     out = learn(state); state = out.learner_state
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    sh = learn.built["shards"][0]
+    traj = O.Trajectory(obs=f64(sh.obs[:T]), action=sh.action.cpu().numpy(), reward=f64(sh.reward),
+                        done=sh.done.cpu().numpy().astype(bool), truncated=sh.truncated.cpu().numpy().astype(bool), next_obs=f64(sh.next_obs))
+    O.evaluate_rollout(actor, critic, traj, bf16=bf16)
+    if bf16:
+        traj.value, traj.bootstrap_value, traj.log_prob = f64(sh.value), f64(sh.bootstrap_value), f64(sh.log_prob)
+    perms = np.stack([ops.make_permutation(T * E, state.key[1], ep + 4 * upd, device="cuda").cpu().numpy() for ep in range(4)])
+    actor, critic, metrics, _, _ = O.ppo_update(actor, critic, a_st, c_st, traj, perms, h, grad_sync=grad_sync, bf16=bf16)
+    a_tree, c_tree = state.params.actor_params, state.params.critic_params
+    _, coff, _ = ops.arena_offsets(a_tree.spec, c_tree.spec)
+    mu, nu = f64(a_tree.arena_mu), f64(a_tree.arena_nu)
+    mom = max(rel(mu[:n_a], a_st.mu), rel(nu[:n_a], a_st.nu), rel(mu[coff:coff + n_c], c_st.mu), rel(nu[coff:coff + n_c], c_st.nu))
+    worst["moments_rel"] = max(worst["moments_rel"], mom)
+    pa, pc = f64(a_tree.flat), f64(c_tree.flat)
+    worst["params_abs"] = max(worst["params_abs"], float(np.abs(pa - actor.flat()).max()), float(np.abs(pc - critic.flat()).max()))
+    for name in ("actor_loss", "entropy", "value_loss"):
+        got, ref = f64(out.train_metrics[name][0]), metrics[name]
+        worst["metrics_rel"] = max(worst["metrics_rel"], float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6)))
+    if bf16:
+        # tcgen05 path vs the bf16-rounding oracle: moments norm-wise 1e-2 (tests/test_tc_gpu.py); the oracle continues
+        # from the kernels' parameters so that the three updates are checked independently
+        if mom > 1e-2: ok, why = False, f"update {upd}: Adam moments rel {mom:.3e}"
+        actor, critic = tree(a_tree), tree(c_tree)
+        a_st.mu, a_st.nu, c_st.mu, c_st.nu = mu[:n_a].copy(), nu[:n_a].copy(), mu[coff:coff + n_c].copy(), nu[coff:coff + n_c].copy()
+    else:
+        # fp32 CUDA-core path vs the fp64 oracle: the single-device tolerance (tests/test_learner_gpu.py)
+        if not (np.allclose(pa, actor.flat(), rtol=1e-4, atol=2e-6) and np.allclose(pc, critic.flat(), rtol=1e-4, atol=2e-6)):
+            ok, why = False, f"update {upd}: parameters differ from the oracle by {worst['params_abs']:.3e}"
 arena = state.params.actor_params.arena
 gathered = [torch.empty_like(arena) for _ in range(world)]
 dist.all_gather(gathered, arena)
 obs_sum = learn.built["shards"][0].obs[:T].float().sum()
 sums = [torch.empty_like(obs_sum) for _ in range(world)]
 dist.all_gather(sums, obs_sum)
+flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    same = all(torch.equal(gathered[0], g) for g in gathered)
-    print(json.dumps({"params_identical_across_ranks": same, "changed": not torch.equal(p0, arena), "finite": bool(torch.isfinite(arena).all()),
+    print(json.dumps({"oracle_ok_all_ranks": bool(flags.item() == 1.0), "why": why, **worst,
+                      "params_identical_across_ranks": all(torch.equal(gathered[0], g) for g in gathered),
                       "shards_differ": len({float(s) for s in sums}) == world, "fused_used": learn.built["peers_obj"] is not None,
-                      "arena_sum": float(arena.double().sum()),
-                      "value_loss": float(out.train_metrics["value_loss"].mean())}))
+                      "counts": state.params.actor_params.arena_counts.cpu().tolist()}))
 dist.barrier(); torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)  # NCCL teardown can hang at exit here
 '''
 
 
 @pytest.mark.parametrize("precision,fused", [("f32", "False"), ("bf16", "False"), ("bf16", "True"), ("f32", "True")])
-def test_two_rank_update_keeps_replicas_identical(precision, fused, tmp_path):
+def test_two_rank_update_matches_oracle(precision, fused, tmp_path):
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip("NEEDS 2 GPUs (NCCL refuses two ranks on one device): run `gpurun --gpus 2 -- python -m pytest "
+                    "tests/test_distributed_gpu.py -m gpu`; the fused all-reduce kernel itself is covered on one device by "
+                    "test_fused_allreduce_kernel_on_one_device")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29511", str(script), precision, fused]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    import json
-
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
-    assert res["params_identical_across_ranks"] and res["changed"] and res["finite"] and res["shards_differ"], res
-    assert res["fused_used"] == (fused == "True"), res
     print(res)
+    assert res["oracle_ok_all_ranks"], res
+    assert res["params_identical_across_ranks"] and res["shards_differ"], res
+    assert res["fused_used"] == (fused == "True"), res
+    assert res["counts"] == [3 * 4 * 4] * 4, res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_allreduce_kernel_on_one_device(world):
+    """`stx_allreduce_clip_adam_step` with `world` virtual ranks on ONE device.  Each virtual rank owns a gradient arena,
+    a signal pad, parameters, moments, counters and scratch; the kernels run one after the other, so before virtual rank r's
+    launch the test itself writes the announcements of the ranks that have not run yet into r's pad (their gradients ARE
+    complete: the test wrote them).  Three calls, so that the generation counter, bias correction and LR schedule advance."""
+    from oracle import ppo_oracle as O
+    from stoix_b200 import _lib, ops
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(world)
+    sa, sc = ops.MlpSpec((12, 32, 32, 5)), ops.MlpSpec((12, 32, 32, 1))
+    _, coff, total = ops.arena_offsets(sa, sc)
+    n_a, n_c = sa.param_count, sc.param_count
+    p0 = np.zeros(total, np.float32)
+    p0[:n_a] = rng.standard_normal(n_a) * 0.3
+    p0[coff:coff + n_c] = rng.standard_normal(n_c) * 0.3
+    segs = [(0, n_a, 3e-3, 0.5), (coff, n_c, 1e-3, 0.05)]  # the critic optimiser clips
+    lib = _lib.load()
+    slot, pad_words = 16, 64
+    ranks = []
+    for r in range(world):
+        ranks.append(dict(
+            params=torch.tensor(p0, device=dev), mu=torch.zeros(total, device=dev), nu=torch.zeros(total, device=dev),
+            grads=torch.zeros(total, device=dev), gsum=torch.zeros(total, device=dev), pad=torch.zeros(pad_words, dtype=torch.int32, device=dev),
+            plan=ops.AdamPlan(segs, dev, decay=True, steps_per_update=2, num_updates=4)))
+    grad_ptrs = (C.c_void_p * world)(*[rk["grads"].data_ptr() for rk in ranks])
+    pad_ptrs = (C.c_void_p * world)(*[rk["pad"].data_ptr() for rk in ranks])
+    ref_p = [p0[:n_a].astype(np.float64), p0[coff:coff + n_c].astype(np.float64)]
+    ref_st = [O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c))]
+    for call in range(1, 4):
+        g_np = [np.zeros(total, np.float32) for _ in range(world)]
+        for r in range(world):
+            g_np[r][:n_a] = rng.standard_normal(n_a) * 0.05
+            g_np[r][coff:coff + n_c] = rng.standard_normal(n_c) * (0.5 if r == 0 else 0.05)
+            ranks[r]["grads"].copy_(torch.tensor(g_np[r]))
+        for r in range(world):
+            rk = ranks[r]
+            rk["pad"][slot:slot + world] = call  # the virtual ranks that run later have (logically) announced already
+            rk["plan"].hyper.grad_scale = 1.0 / world
+            rk["plan"].hyper.prenorm = 0
+            rc = lib.stx_allreduce_clip_adam_step(C.c_void_p(rk["params"].data_ptr()), grad_ptrs, pad_ptrs, world, r, slot,
+                                                  C.c_void_p(rk["gsum"].data_ptr()), C.c_void_p(rk["mu"].data_ptr()), C.c_void_p(rk["nu"].data_ptr()),
+                                                  C.c_void_p(rk["plan"].counts.data_ptr()), C.c_void_p(rk["plan"].segs.data_ptr()), rk["plan"].nseg,
+                                                  C.byref(rk["plan"].hyper), None, C.c_void_p(rk["plan"].gnorm.data_ptr()),
+                                                  C.c_void_p(rk["plan"].scratch.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc, "stx_allreduce_clip_adam_step")
+            torch.cuda.synchronize()
+            assert int(rk["pad"][slot + r].item()) == call  # its own announcement arrived in its own pad too
+        mean = np.mean(np.stack([g.astype(np.float64) for g in g_np]), axis=0)
+        for s, (off, cnt, lr, mgn) in enumerate(segs):
+            k = ref_st[s].sched_count // 2
+            ref_p[s], gnorm = O.clip_adam_step(ref_p[s], mean[off:off + cnt], ref_st[s], lr * (1.0 - k / 4), mgn)
+            for r in range(world):
+                rk = ranks[r]
+                np.testing.assert_allclose(rk["params"][off:off + cnt].cpu().numpy(), ref_p[s], rtol=2e-5, atol=2e-7)
+                np.testing.assert_allclose(rk["mu"][off:off + cnt].cpu().numpy(), ref_st[s].mu, rtol=2e-5, atol=1e-9)
+                np.testing.assert_allclose(rk["nu"][off:off + cnt].cpu().numpy(), ref_st[s].nu, rtol=2e-5, atol=1e-12)
+                np.testing.assert_allclose(float(rk["plan"].gnorm[s].item()), gnorm, rtol=1e-5)
+        for r in range(1, world):  # identical association order on every rank => bit-identical replicas
+            for k in ("params", "mu", "nu", "gsum"):
+                assert torch.equal(ranks[0][k], ranks[r][k]), f"virtual rank {r}: {k} differs from rank 0 after call {call}"
+        assert ranks[0]["plan"].counts.cpu().tolist() == [call] * 4

@@ -67,6 +67,9 @@ def _rel(a, b):
     (512, 128, 256, 32, 5, False),
     (16384, 0, 16384, 64, 8, True),   # > 1 tile per CTA, every split-K CTA busy
     (384, 0, 128, 64, 16, True),      # a single tile: most CTAs idle
+    # BASELINE config 2 (the shape bench.py runs): B = T*E = 524 288 rows, minibatch 32 768 = 256 tiles per
+    # network (3.46 tiles per K3a CTA, every split-K CTA with >= 7 chunks), shuffle indices up to 2^19
+    (524288, 5 * 32768, 32768, 64, 8, True),
 ])
 def test_tc_ppo_minibatch_grads_vs_bf16_oracle(B, mb_off, mb, D, A, use_perm):
     """K3 on tensor cores vs the oracle with the same bf16 operand rounding (weights, activations, dY);
@@ -129,26 +132,45 @@ def test_tc_ppo_minibatch_grads_vs_bf16_oracle(B, mb_off, mb, D, A, use_perm):
                             precision=ops.STX_PREC_BF16, param_arena_bf16=shadow)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(grads.cpu().numpy(), (2 * g).astype(np.float32))
-    # bf16 path vs the pure fp32 reference gradient: reported band (2e-2)
-    lg32, acts32 = O.mlp_forward(actor, obs.astype(np.float64)[idx])
+    # bf16 path vs the PURE fp32/fp64 oracle (no operand rounding anywhere): the stated tolerance of the tensor-core
+    # path against the reference arithmetic.  bf16 operands carry 2^-9 relative rounding; the gradient is a
+    # cancellation-heavy sum over the minibatch, so the bound is norm-wise per network: relative error <= 0.1
+    # (cosine >= 0.995).  Measured values are printed (typically 0.02-0.06).
+    obs64 = obs.astype(np.float64)[idx]
+    lg32, acts32 = O.mlp_forward(actor, obs64)
     _, dlg32, _ = O.actor_loss_and_dlogits(lg32, act[idx], lp_old[idx].astype(np.float64), adv_n[idx], 0.2, 0.01)
     ga32 = O.mlp_backward(actor, acts32, dlg32).flat()
-    cos = float(g[: sa.param_count] @ ga32 / (np.linalg.norm(g[: sa.param_count]) * np.linalg.norm(ga32)))
-    print(f"bf16-path actor gradient vs pure fp32 gradient: rel {_rel(g[: sa.param_count], ga32):.3f}, cosine {cos:.4f}")
-    assert cos > 0.97  # bf16 operand rounding on a cancellation-heavy sum; reported, not a parity bound
+    v32, cacts32 = O.mlp_forward(critic, obs64)
+    _, dv32, _ = O.critic_loss_and_dvalue(v32[:, 0], v_old[idx].astype(np.float64), tgt[idx].astype(np.float64), 0.2, 0.5)
+    gc32 = O.mlp_backward(critic, cacts32, dv32[:, None]).flat()
+    for label, got, ref32 in (("actor", g[: sa.param_count], ga32), ("critic", g[coff : coff + sc.param_count], gc32)):
+        cos = float(got @ ref32 / (np.linalg.norm(got) * np.linalg.norm(ref32)))
+        rel = _rel(got, ref32)
+        print(f"bf16-path {label} gradient vs pure fp32 oracle: norm-wise rel {rel:.4f}, cosine {cos:.5f}")
+        assert rel < 0.1 and cos > 0.995, f"{label}: bf16 path vs fp32 oracle rel {rel:.4f} cos {cos:.5f}"
 
 
-def test_learner_bf16_update_tracks_bf16_oracle():
-    """One whole Anakin update step with arch.precision=bf16 (tcgen05 rollout forward, batched critic,
-    K3 on tensor cores, bf16 weight shadows refreshed by the fused Adam) vs the oracle run with the same
-    bf16 operand rounding, actions and permutations injected."""
+@pytest.mark.parametrize("E,T,nmb", [
+    (64, 8, 2),
+    (4096, 128, 16),   # BASELINE config 2: the exact update step bench.py times (mb = 32 768, 64 optimiser steps)
+])
+def test_learner_bf16_update_tracks_bf16_oracle(E, T, nmb):
+    """One whole Anakin update step with arch.precision=bf16 (tcgen05 rollout, batched critic, K3 on tensor
+    cores, bf16 weight shadows refreshed by the fused Adam) vs the oracle run with the same bf16 operand
+    rounding, actions and permutations injected.
+
+    Bounds.  Adam's first / second moments are linear / quadratic in the gradients, so they are compared
+    norm-wise at 1e-2 per network after all epochs x minibatches optimiser steps (what is left between the
+    kernels and the oracle is fp32 summation order, fast-math exp/log in the loss epilogue and rare 1-ulp bf16
+    rounding flips of a hidden activation).  The parameter CHANGE is reported and bounded at 5e-2 norm-wise:
+    Adam turns every entry's gradient into a step of ~lr whatever its size, so entries whose (tiny) gradient
+    differs in the last bits move differently."""
     from stoix_b200 import ops, random as srandom
     from stoix_b200.config import compose
     from stoix_b200.systems.ppo.anakin import ff_ppo
     from stoix_b200.utils import make_env
     from stoix_b200.utils.total_timestep_checker import check_total_timesteps
 
-    E, T, nmb = 64, 8, 2
     cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E}", f"system.rollout_length={T}",
                                      f"system.num_minibatches={nmb}", f"arch.total_timesteps={E * T * 2}", "arch.num_evaluation=1",
                                      "arch.precision=bf16", "logger.use_console=False", "env.kwargs.p_term=0.05", "env.kwargs.p_trunc=0.05"])
@@ -175,22 +197,35 @@ def test_learner_bf16_update_tracks_bf16_oracle():
     O.evaluate_rollout(actor, critic, traj, bf16=True)
     np.testing.assert_allclose(f64(sh.value), traj.value, rtol=2e-3, atol=2e-2)
     np.testing.assert_allclose(f64(sh.log_prob), traj.log_prob, rtol=2e-3, atol=2e-2)
+    np.testing.assert_allclose(f64(sh.bootstrap_value), traj.bootstrap_value, rtol=2e-3, atol=2e-2)
     perms = np.stack([ops.make_permutation(T * E, state.key[1], ep, device="cuda").cpu().numpy() for ep in range(4)])
+    for ep in range(4):  # the learner consumed exactly these shuffles, and each is a bijection of the flat index
+        assert np.array_equal(perms[ep], sh.perms[ep].cpu().numpy())
+        assert np.array_equal(np.sort(perms[ep]), np.arange(T * E))
     h = O.PPOHyper(num_minibatches=nmb, num_updates=int(cfg.arch.num_updates))
     # feed the oracle the kernel's own value / log_prob so both run the update from identical inputs
     traj.value, traj.bootstrap_value, traj.log_prob = f64(sh.value), f64(sh.bootstrap_value), f64(sh.log_prob)
     n_a, n_c = actor.flat().size, critic.flat().size
-    a2, c2, metrics, adv, tgt = O.ppo_update(actor, critic, O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c)),
-                                             traj, perms, h, bf16=True)
+    a_st, c_st = O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c))
+    a2, c2, metrics, adv, tgt = O.ppo_update(actor, critic, a_st, c_st, traj, perms, h, bf16=True)
     np.testing.assert_allclose(f64(sh.targets), tgt, rtol=1e-4, atol=2e-5)
-    da, dc = f64(out.learner_state.params.actor_params.flat) - p0a, f64(out.learner_state.params.critic_params.flat) - p0c
+    a_tree = out.learner_state.params.actor_params
+    _, coff, _ = ops.arena_offsets(a_tree.spec, out.learner_state.params.critic_params.spec)
+    mu, nu = f64(a_tree.arena_mu), f64(a_tree.arena_nu)
+    errs = {
+        "actor mu": _rel(mu[:n_a], a_st.mu), "actor nu": _rel(nu[:n_a], a_st.nu),
+        "critic mu": _rel(mu[coff:coff + n_c], c_st.mu), "critic nu": _rel(nu[coff:coff + n_c], c_st.nu),
+    }
+    da, dc = f64(a_tree.flat) - p0a, f64(out.learner_state.params.critic_params.flat) - p0c
     ra, rc = _rel(da, a2.flat() - p0a), _rel(dc, c2.flat() - p0c)
-    print(f"parameter change after 8 Adam steps, bf16 kernels vs bf16 oracle: actor rel {ra:.3e}, critic rel {rc:.3e}")
-    # Adam turns every gradient entry into a step of size ~lr, so entries whose tiny gradients differ in the
-    # last bits move differently; the bulk of the update must agree.
-    assert ra < 0.1 and rc < 0.1
-    shadow = out.learner_state.params.actor_params.arena_bf16
-    assert torch.equal(shadow, out.learner_state.params.actor_params.arena.to(torch.bfloat16))
+    print(f"E={E} T={T}: after {4 * nmb} Adam steps, bf16 kernels vs bf16 oracle: " + ", ".join(f"{k} rel {v:.2e}" for k, v in errs.items())
+          + f"; parameter change actor rel {ra:.3e}, critic rel {rc:.3e}")
+    for k, v in errs.items():
+        assert v < 1e-2, f"{k}: norm-wise relative error {v:.3e} of the Adam moment after {4 * nmb} steps"
+    assert ra < 5e-2 and rc < 5e-2, (ra, rc)
+    assert a_tree.arena_counts.cpu().tolist() == [4 * nmb] * 4
+    shadow = a_tree.arena_bf16
+    assert torch.equal(shadow, a_tree.arena.to(torch.bfloat16))
     for name in ("actor_loss", "entropy", "value_loss"):
         np.testing.assert_allclose(f64(out.train_metrics[name][0]), metrics[name], rtol=2e-2, atol=2e-3)
 
