@@ -89,7 +89,33 @@ struct FbParams {
   int D;
   int mb;
   float clip_eps, ent_coef, vf_coef;
+  // fused launch (tc_ppo_fused_kernel): per-tile completion counters polled by the weight-gradient CTAs (nullptr: none)
+  uint32_t* flag_a;   // [2][tiles] h1, h2, dz, dh2 of (net, tile) stored      -> kFlagEpi arrivals (one per epilogue warp)
+  uint32_t* flag_b;   // [2][tiles] dh1 of (net, tile) stored                  -> kFlagEpi arrivals
+  uint32_t* flag_x;   // [tiles]    gathered input rows xg of tile stored      -> kFlagGather arrivals (actor CTAs)
 };
+constexpr uint32_t kFlagEpi = 8, kFlagGather = 4;
+
+// Release "this warp's stores of the tile are issued" to the consumer CTAs: the warp barrier orders the other lanes' stores
+// before lane 0's gpu-scope fence (the same barrier + single-thread fence pattern cooperative-groups grid.sync relies on).
+__device__ __forceinline__ void flag_signal(uint32_t* f, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+  }
+}
+// Consumer side (one thread): spin until `want` arrivals, then order the async-proxy (TMA) reads that follow behind it.
+__device__ __forceinline__ void flag_wait(const uint32_t* f, uint32_t want, const char* what) {
+  uint32_t v, spins = 0;
+  unsigned long long t0 = 0ull;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v >= want) break;
+    spin_guard(spins, t0, what);
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 
 // Tiled activation layout shared by K3a (writer) and K3b (reader): element (row, col) of a [mb x 8*CG]
 // matrix lives at ((row/128 * CG + col/8) * 128 + row%128) * 8 + col%8.
@@ -158,12 +184,10 @@ __device__ __forceinline__ void actor_head(const uint32_t (&r)[16], const float*
   ent_out = ent;
 }
 
+// The K3a CTA: called by tc_ppo_fwd_bwd_kernel (split launches) and by the producer CTAs of tc_ppo_fused_kernel.
 template <int NEPI>
-__global__ void __launch_bounds__(fb_threads(NEPI), 1)
-    tc_ppo_fwd_bwd_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
-                          const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
-                          const FbParams p) {
-  extern __shared__ uint8_t smem_raw[];
+__device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tmW0a, const CUtensorMap& tmW1a, const CUtensorMap& tmW0c,
+                                        const CUtensorMap& tmW1c, const FbParams& p) {
   // align by OFFSET (not through an integer cast) so that the compiler keeps the shared address space: LDS/STS, not generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
@@ -288,6 +312,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
       if (warp == 0) STX_STAMP(51);
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_full[s]);
+      if (which == 0 && p.flag_x != nullptr) flag_signal(p.flag_x + tile, lane);  // xg rows of this warp are on their way
     }
   } else if (warp == kFbMmaWarp) {
     // ===================== MMA issuer =====================
@@ -467,6 +492,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
+          // the flushes above issued this warp's last dh1 stores of the PREVIOUS tile: dh1 of that tile is complete
+          if (layer == 0 && cc == 0 && it > 0 && p.flag_b != nullptr) flag_signal(p.flag_b + which * num_tiles + (tile - ncta), lane);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
           pend_ptr = tiled_ptr(hout, mrow, c * 4, 32);
@@ -572,6 +599,8 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
+          // first chunk of E4: the flushes above issued this warp's last dh2 stores; h1, h2 and dz went out earlier
+          if (layer == 0 && cc == 0 && p.flag_a != nullptr) flag_signal(p.flag_a + which * num_tiles + tile, lane);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
           pend_ptr = tiled_ptr(dout, mrow, c * 4, 32);
@@ -586,6 +615,7 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) STX_FLUSH_PENDING(g);  // the last chunk of the last tile
+    if (my_tiles > 0 && p.flag_b != nullptr) flag_signal(p.flag_b + which * num_tiles + cta_in_net + (my_tiles - 1) * ncta, lane);
 #undef STX_FLUSH_PENDING
     STX_STAMP_AT(61, warp == 5 && lane == 0);
   }
@@ -617,6 +647,15 @@ __global__ void __launch_bounds__(fb_threads(NEPI), 1)
   STX_STAMP_AT(62, threadIdx.x == 0);
 }
 
+template <int NEPI>
+__global__ void __launch_bounds__(fb_threads(NEPI), 1)
+    tc_ppo_fwd_bwd_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
+                          const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
+                          const FbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  fb_role<NEPI>(smem_raw, tmW0a, tmW1a, tmW0c, tmW1c, p);
+}
+
 // =============================== K3b: dW = A^T * B ===============================================
 constexpr int kDwThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kDwStages = 3;
@@ -625,28 +664,45 @@ constexpr uint32_t kDwOffOnes = kDwStages * kDwStageBytes;  // 2 KB: B tile [2 c
 constexpr uint32_t kDwOffBar = kDwOffOnes + 2048;
 constexpr uint32_t kDwSmemBytes = kDwOffBar + 128 + 1024;
 constexpr int kMaxJobs = 6;
+constexpr int kMaxSubs = 2;
 
-struct DwJob {
+// One weight-gradient GEMM of a job: dW = A^T * B over the rows this CTA is given.
+struct DwSub {
   float* part;     // [n_cta][256 x N] fp32 partial outputs
-  int N;           // 16, 64 or 256 (= 8 * column groups of B)
-  int cta_begin;   // first CTA of this job
-  int n_cta;
-  int num_chunks;  // mb / 64
   float* colsum;   // nullable: [n_cta][256] per-CTA sums over the rows of every A column (A^T * 1): the bias gradient that
                    // belongs to A = dh1, obtained from one extra N=16 MMA per K step against an all-ones B tile
+  int N;           // 16, 64 or 256 (= 8 * column groups of B)
+  int map;         // index of the (A, B) tensor-map pair in DwMaps
+  int tmem_col;    // accumulator columns [tmem_col, tmem_col + N (+16 with colsum)) of each 256-column half
+  int wait_b;      // fused launch: 0 = operands complete with flag_a; 1 = needs flag_b (dh1) and flag_x (xg) as well
+};
+// A job = the CTAs [cta_begin, cta_begin + n_cta) running the same 1..2 GEMMs over an interleaved share of the 64-row chunks.
+struct DwJob {
+  DwSub sub[kMaxSubs];
+  int n_sub;
+  int cta_begin;   // first CTA of this job (relative to the first weight-gradient CTA of the launch)
+  int n_cta;
+  int num_chunks;  // mb / 64
+  int net;
 };
 struct DwParams {
   DwJob job[kMaxJobs];
   int n_jobs;
+  int num_tiles;
+  // fused launch: completion counters written by the K3a CTAs of the same grid (nullptr: operands are complete at entry)
+  const uint32_t* flag_a;
+  const uint32_t* flag_b;
+  const uint32_t* flag_x;
 };
 struct DwMaps {
   CUtensorMap a[kMaxJobs];  // tiled [mb x 256]: 2D u64 view {256 per (tile, colgroup), tiles*32}, box {128, 32}
   CUtensorMap b[kMaxJobs];  // tiled [mb x N]:   box {128, N/8}
 };
 
-__global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// The K3b CTA (warps 0..5 of the block work; further warps of a fused launch only join the block barriers).
+// `cta` counts from the first weight-gradient CTA of the launch.
+__device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, const DwParams& p, const int cta_abs, const bool fused) {
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwOffBar);
   uint64_t* full = bars;                 // [kDwStages]
@@ -656,12 +712,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int j = 0;
-  while (j + 1 < p.n_jobs && (int)blockIdx.x >= p.job[j + 1].cta_begin) ++j;
+  while (j + 1 < p.n_jobs && cta_abs >= p.job[j + 1].cta_begin) ++j;
   const DwJob& job = p.job[j];
-  const int cta = (int)blockIdx.x - job.cta_begin;
+  const int cta = cta_abs - job.cta_begin;
   const int my_chunks = cta < job.num_chunks ? (job.num_chunks - cta + job.n_cta - 1) / job.n_cta : 0;
-  const int cgb = job.N >> 3;  // column groups of B
-  const uint32_t stage_tx = 32768 + (uint32_t)job.N * 128;
+  const int n_sub = job.n_sub;
+  const int my_iters = my_chunks * n_sub;  // pipeline slots: (chunk, sub-GEMM) pairs in order
+  bool any_colsum = false;
+  for (int sj = 0; sj < n_sub; ++sj) any_colsum |= job.sub[sj].colsum != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -670,13 +728,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     }
     mbar_init(acc_done, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&maps.a[j]);
-    tma_prefetch_desc(&maps.b[j]);
+    for (int sj = 0; sj < n_sub; ++sj) {
+      tma_prefetch_desc(&maps.a[job.sub[sj].map]);
+      tma_prefetch_desc(&maps.b[job.sub[sj].map]);
+    }
   }
   griddep_launch();
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (job.colsum != nullptr) {  // all-ones B operand (every layout of a constant tile is the same tile)
-    for (int i = threadIdx.x; i < 512; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + kDwOffOnes)[i] = 0x3F803F80u;
+  if (any_colsum) {  // all-ones B operand (every layout of a constant tile is the same tile)
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kDwOffOnes)[i] = 0x3F803F80u;
     fence_async_proxy();
   }
   tc_fence_before();
@@ -688,83 +748,104 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
   if (warp == 0) {
     if (elect_one()) {
       const uint64_t pol_stream = l2_evict_first();  // every activation tile is read exactly once
+      int k = 0;
       for (int it = 0; it < my_chunks; ++it) {
-        const int s = it % kDwStages;
-        if (it >= kDwStages) mbar_wait(&empty[s], ((it / kDwStages) & 1) ^ 1, 20);
-        // newest rows first: K3a wrote the last tiles most recently, so they are the likeliest L2 residents
-        const int chunk = job.num_chunks - 1 - (cta + it * job.n_cta);  // 64 rows: half of a 128-row tile
+        // split launches: newest rows first (K3a wrote the last tiles most recently, so they are the likeliest L2 residents);
+        // fused launch: in the order the K3a CTAs of this grid finish their tiles
+        const int ci = cta + it * job.n_cta;
+        const int chunk = fused ? ci : job.num_chunks - 1 - ci;  // 64 rows: half of a 128-row tile
         const int tile = chunk >> 1, r0 = (chunk & 1) * 64;
-        uint8_t* st = smem + s * kDwStageBytes;
-        mbar_arrive_expect_tx(&full[s], stage_tx);
-        // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
-        tma_load_2d_hint(st, &maps.a[j], &full[s], r0 * 2, tile * 32, pol_stream);
-        tma_load_2d_hint(st + 32768, &maps.b[j], &full[s], r0 * 2, tile * cgb, pol_stream);
+        for (int sj = 0; sj < n_sub; ++sj, ++k) {
+          const DwSub& sub = job.sub[sj];
+          const int s = k % kDwStages;
+          if (k >= kDwStages) mbar_wait(&empty[s], ((k / kDwStages) & 1) ^ 1, 20);
+          if (fused) {
+            flag_wait(p.flag_a + job.net * p.num_tiles + tile, kFlagEpi, "K3 activations (h1, h2, dz, dh2) of a tile");
+            if (sub.wait_b) {
+              flag_wait(p.flag_b + job.net * p.num_tiles + tile, kFlagEpi, "K3 activations (dh1) of a tile");
+              flag_wait(p.flag_x + tile, kFlagGather, "K3 gathered input rows of a tile");
+            }
+          }
+          uint8_t* st = smem + s * kDwStageBytes;
+          mbar_arrive_expect_tx(&full[s], 32768 + (uint32_t)sub.N * 128);
+          // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
+          tma_load_2d_hint(st, &maps.a[sub.map], &full[s], r0 * 2, tile * 32, pol_stream);
+          tma_load_2d_hint(st + 32768, &maps.b[sub.map], &full[s], r0 * 2, tile * (sub.N >> 3), pol_stream);
+        }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_bf16(128, job.N, 1, 1);  // both operands MN-major
     constexpr uint32_t idesc_ones = idesc_bf16(128, 16, 1, 1);
-    const bool colsum = job.colsum != nullptr;
+    int k = 0;
     for (int it = 0; it < my_chunks; ++it) {
-      const int s = it % kDwStages;
-      mbar_wait(&full[s], (it / kDwStages) & 1, 21);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a0 = sbase + s * kDwStageBytes, b0 = a0 + 32768;
+      for (int sj = 0; sj < n_sub; ++sj, ++k) {
+        const DwSub& sub = job.sub[sj];
+        const uint32_t idesc = idesc_bf16(128, sub.N, 1, 1);  // both operands MN-major
+        const bool colsum = sub.colsum != nullptr;
+        const int s = k % kDwStages;
+        mbar_wait(&full[s], (k / kDwStages) & 1, 21);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = sbase + s * kDwStageBytes, b0 = a0 + 32768;
+          const uint32_t acc = (it > 0) ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {      // 16 rows (K) per step = two core-matrix row groups of 128 B
+          for (int ks = 0; ks < 4; ++ks) {      // 16 rows (K) per step = two core-matrix row groups of 128 B
 #pragma unroll
-          for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128) = column groups 16 h ..
-            mma_ss(tmem + h * 256, smem_desc(a0 + h * 16384 + k * 256, 128, 1024, SWIZZLE_NONE),
-                   smem_desc(b0 + k * 256, 128, 1024, SWIZZLE_NONE), idesc, (it > 0 || k > 0) ? 1u : 0u);
-          if (colsum) {
+            for (int h = 0; h < 2; ++h)      // M halves: hidden units [128 h, 128 h + 128) = column groups 16 h ..
+              mma_ss(tmem + h * 256 + sub.tmem_col, smem_desc(a0 + h * 16384 + ks * 256, 128, 1024, SWIZZLE_NONE),
+                     smem_desc(b0 + ks * 256, 128, 1024, SWIZZLE_NONE), idesc, (acc | (uint32_t)(ks > 0)));
+            if (colsum) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)  // columns [N, N+16) of each half: A^T * ones (every column holds the same sums)
-              mma_ss(tmem + h * 256 + job.N, smem_desc(a0 + h * 16384 + k * 256, 128, 1024, SWIZZLE_NONE),
-                     smem_desc(sbase + kDwOffOnes, 128, 1024, SWIZZLE_NONE), idesc_ones, (it > 0 || k > 0) ? 1u : 0u);
+              for (int h = 0; h < 2; ++h)  // columns [N, N+16) behind the GEMM's: A^T * ones (every column holds the same sums)
+                mma_ss(tmem + h * 256 + sub.tmem_col + sub.N, smem_desc(a0 + h * 16384 + ks * 256, 128, 1024, SWIZZLE_NONE),
+                       smem_desc(sbase + kDwOffOnes, 128, 1024, SWIZZLE_NONE), idesc_ones, (acc | (uint32_t)(ks > 0)));
+            }
           }
+          mma_commit(&empty[s]);
         }
-        mma_commit(&empty[s]);
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (elect_one()) mma_commit(acc_done);
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     const int q = warp & 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    // partial layout [N/4][256 rows][4]: the 32 lanes of a warp (= 32 consecutive rows) write 512 contiguous bytes
-    float4* out = reinterpret_cast<float4*>(job.part + (int64_t)cta * 256 * job.N);
     const uint64_t pol_keep = l2_evict_last();  // the reduce kernel reads these next: keep them in L2 under the activation stream
-    if (my_chunks > 0) {
+    if (my_iters > 0) {
       mbar_wait(acc_done, 0, 22);
       tc_fence_after();
     }
-    for (int h = 0; h < 2; ++h) {
-      const int m = h * 128 + q * 32 + lane;
-      for (int c = 0; c < job.N / 16; ++c) {
-        uint32_t r[16];
-        if (my_chunks > 0) {
-          tmem_ld16(tmem + lane_addr + h * 256 + c * 16, r);
-          tmem_ld_wait();
-        } else {
+    for (int sj = 0; sj < n_sub; ++sj) {
+      const DwSub& sub = job.sub[sj];
+      // partial layout [N/4][256 rows][4]: the 32 lanes of a warp (= 32 consecutive rows) write 512 contiguous bytes
+      float4* out = reinterpret_cast<float4*>(sub.part + (int64_t)cta * 256 * sub.N);
+      for (int h = 0; h < 2; ++h) {
+        const int m = h * 128 + q * 32 + lane;
+        for (int c = 0; c < sub.N / 16; ++c) {
+          uint32_t r[16];
+          if (my_iters > 0) {
+            tmem_ld16(tmem + lane_addr + h * 256 + sub.tmem_col + c * 16, r);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = 0u;
-        }
+            for (int i = 0; i < 16; ++i) r[i] = 0u;
+          }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_hint(&out[(int64_t)(c * 4 + i) * 256 + m],
-                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
-                  pol_keep);
-      }
-      if (job.colsum != nullptr) {
-        uint32_t r[16];
-        r[0] = 0u;
-        if (my_chunks > 0) {
-          tmem_ld16(tmem + lane_addr + h * 256 + job.N, r);
-          tmem_ld_wait();
+          for (int i = 0; i < 4; ++i)
+            st_hint(&out[(int64_t)(c * 4 + i) * 256 + m],
+                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
+                    pol_keep);
         }
-        st_hint(&job.colsum[(int64_t)cta * 256 + m], __uint_as_float(r[0]), pol_keep);
+        if (sub.colsum != nullptr) {
+          uint32_t r[16];
+          r[0] = 0u;
+          if (my_iters > 0) {
+            tmem_ld16(tmem + lane_addr + h * 256 + sub.tmem_col + sub.N, r);
+            tmem_ld_wait();
+          }
+          st_hint(&sub.colsum[(int64_t)cta * 256 + m], __uint_as_float(r[0]), pol_keep);
+        }
       }
     }
   }
@@ -774,6 +855,27 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  dw_role(smem_raw, maps, p, (int)blockIdx.x, false);
+}
+
+// ONE launch for K3a + K3b: the first n_cta[0] + n_cta[1] CTAs are K3a CTAs (fb_role), the rest weight-gradient CTAs
+// (dw_role) that consume the activation tiles as the K3a CTAs of the same grid complete them (flag_a / flag_b / flag_x),
+// through L2 instead of after a kernel boundary.  All CTAs are co-resident (grid <= 148, one CTA per SM); a consumer only
+// ever waits for K3a CTAs, which wait for nobody outside their own CTA, so the launch cannot deadlock.  The assignment of
+// tiles to CTAs is static => the partial sums keep a fixed association order (run-to-run deterministic gradients).
+template <int NEPI>
+__global__ void __launch_bounds__(fb_threads(NEPI), 1)
+    tc_ppo_fused_kernel(const __grid_constant__ CUtensorMap tmW0a, const __grid_constant__ CUtensorMap tmW1a,
+                        const __grid_constant__ CUtensorMap tmW0c, const __grid_constant__ CUtensorMap tmW1c,
+                        const FbParams p, const __grid_constant__ DwMaps maps, const DwParams dp) {
+  extern __shared__ uint8_t smem_raw[];
+  const int n_fb = p.n_cta[0] + p.n_cta[1];
+  if ((int)blockIdx.x < n_fb) fb_role<NEPI>(smem_raw, tmW0a, tmW1a, tmW0c, tmW1c, p);
+  else dw_role(smem_raw, maps, dp, (int)blockIdx.x - n_fb, true);
 }
 
 // =============================== reduce partials -> gradient arena ================================
@@ -802,6 +904,8 @@ struct RedParams {
   int overwrite;
   double* sumsq;             // nullable: [2][gridDim] block partials of sum((weight*g)^2) per optimiser segment
   unsigned long long* sumsq_count;  // where the number of block partials per segment (= gridDim) is published
+  uint32_t* flags;           // nullable: the fused launch's tile counters, cleared here for the next optimiser step
+  int n_flags;
 };
 
 constexpr int kRedThreads = 288;  // x 592 blocks >= the ~168k gradient entries of the benchmark networks: one element per thread
@@ -837,6 +941,8 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
   griddep_launch();
   griddep_wait();
   const uint64_t pol_keep = l2_evict_last();  // partials and gradients: small, reused every step, latency-critical
+  if (p.flags != nullptr && blockIdx.x == gridDim.x - 1)  // the fused K3 launch that counted them up has completed
+    for (int i = threadIdx.x; i < p.n_flags; i += blockDim.x) p.flags[i] = 0u;
   double sq0 = 0.0, sq1 = 0.0;
   int64_t my_dst = -1;  // FUSED: arena index, value and optimiser segment of this thread's entry
   float my_g = 0.f;
@@ -911,8 +1017,9 @@ __global__ void __launch_bounds__(kRedThreads) tc_reduce_kernel(const RedParams 
       __threadfence();
       const unsigned long long t = atomicAdd(f.arrive, 1ull);
       const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
-      while (*reinterpret_cast<volatile unsigned long long*>(f.arrive) < target) {
-      }
+      unsigned int spins = 0;
+      unsigned long long t0 = 0ull;
+      while (*reinterpret_cast<volatile unsigned long long*>(f.arrive) < target) spin_guard(spins, t0, "reduce+optimiser grid barrier");
       __threadfence();
     }
     __syncthreads();
@@ -974,24 +1081,35 @@ inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 struct TcWs {
   __nv_bfloat16 *h1[2], *h2[2], *dh1[2], *dh2[2], *dz[2], *xg;
   float *part_w1[2], *part_w2[2], *part_w0[2], *db_part[2], *db0_part[2], *metric_part;
+  uint32_t* flags;  // [2][tiles] a, [2][tiles] b, [tiles] x  (fused launch)
   size_t bytes;
 };
 
 constexpr int kCtaPerNet = kNumSMs / 2;              // 74
-// split-K CTAs per job and net (sum = 74), proportional to the bytes each job streams (dW1: h1 + dh2, dW2: h2 + dz,
-// dW0: dh1 + x): K3b is HBM-bound, so the CTAs should finish together.  Tuning switch: STX_DW_SPLIT="w1,w2,w0".
-struct DwSplit {
-  int w1 = 35, w2 = 18, w0 = 21;
-  DwSplit() {
-    const char* e = getenv("STX_DW_SPLIT");
+// Launch plan, per network (x 2 networks = 148 CTAs).
+//  split (STX_K3_FUSED=0): K3a on 74 CTAs, then K3b with 35/18/21 split-K CTAs for dW1 / dW2 / dW0 -- proportional to the
+//    bytes each job streams (dW1: h1 + dh2, dW2: h2 + dz, dW0: dh1 + x): K3b alone is HBM-bound, so the CTAs should finish together.
+//  fused (default): ONE launch; 64 K3a CTAs (256 tiles of the benchmark minibatch = exactly 4 each), 6 CTAs accumulate dW1
+//    (tensor-bound: 2048 MMA cycles per tile) and 4 CTAs dW2 + dW0 + db0 (two GEMMs per chunk, 148 KB per tile).
+//  Tuning switches: STX_DW_SPLIT="w1,w2,w0" (split), STX_K3_SPLIT="fb,w1,w02" (fused), each summing to 74.
+struct K3Plan {
+  int w1 = 35, w2 = 18, w0 = 21;   // split
+  bool fused = true;
+  int fb = 64, fw1 = 6, fw02 = 4;  // fused
+  K3Plan() {
     int a, b, c;
+    const char* e = getenv("STX_DW_SPLIT");
     if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0 && a + b + c == kCtaPerNet) w1 = a, w2 = b, w0 = c;
+    e = getenv("STX_K3_SPLIT");
+    if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0 && a + b + c == kCtaPerNet) fb = a, fw1 = b, fw02 = c;
+    e = getenv("STX_K3_FUSED");
+    if (e && e[0] == '0') fused = false;
   }
 };
-static const DwSplit g_dw_split;
-#define kDwCtaW1 (g_dw_split.w1)
-#define kDwCtaW2 (g_dw_split.w2)
-#define kDwCtaW0 (g_dw_split.w0)
+static const K3Plan g_plan;
+#define kDwCtaW1 (g_plan.w1)
+#define kDwCtaW2 (g_plan.w2)
+#define kDwCtaW0 (g_plan.w0)
 
 TcWs carve_tc(int64_t mb, char* base) {
   TcWs w{};
@@ -1001,17 +1119,21 @@ TcWs carve_tc(int64_t mb, char* base) {
     o += al(bytes);
     return q;
   };
+  const int tiles = (int)(mb / 128);
+  w.flags = (uint32_t*)take((size_t)5 * tiles * 4);  // first: the caller zero-fills the workspace once, the reduce kernel re-zeroes
+  const int n_w1 = g_plan.fused ? g_plan.fw1 : g_plan.w1, n_w2 = g_plan.fused ? g_plan.fw02 : g_plan.w2,
+            n_w0 = g_plan.fused ? g_plan.fw02 : g_plan.w0;
   for (int n = 0; n < 2; ++n) {
     w.h1[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.h2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.dh1[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.dh2[n] = (__nv_bfloat16*)take((size_t)mb * 256 * 2);
     w.dz[n] = (__nv_bfloat16*)take((size_t)mb * 16 * 2);
-    w.part_w1[n] = (float*)take((size_t)kDwCtaW1 * 65536 * 4);
-    w.part_w2[n] = (float*)take((size_t)kDwCtaW2 * 256 * 16 * 4);
-    w.part_w0[n] = (float*)take((size_t)kDwCtaW0 * 256 * 64 * 4);
+    w.part_w1[n] = (float*)take((size_t)n_w1 * 65536 * 4);
+    w.part_w2[n] = (float*)take((size_t)n_w2 * 256 * 16 * 4);
+    w.part_w0[n] = (float*)take((size_t)n_w0 * 256 * 64 * 4);
     w.db_part[n] = (float*)take((size_t)kCtaPerNet * 528 * 4);
-    w.db0_part[n] = (float*)take((size_t)kDwCtaW0 * 256 * 4);
+    w.db0_part[n] = (float*)take((size_t)n_w0 * 256 * 4);
   }
   w.xg = (__nv_bfloat16*)take((size_t)mb * 64 * 2);
   w.metric_part = (float*)take((size_t)kNumSMs * 8 * 4);
@@ -1022,6 +1144,18 @@ TcWs carve_tc(int64_t mb, char* base) {
 bool tc_ppo_shape_ok(const StxMlp* m) {
   return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
          m->sizes[3] >= 1 && m->sizes[3] <= 16;
+}
+
+// max dynamic shared memory opt-in, once per device and kernel
+template <typename K>
+static int opt_in_smem(K kernel, uint32_t bytes, int slot) {
+  static unsigned long long done[4] = {0, 0, 0, 0};  // bit d of done[slot]: set on device d
+  int dev = 0;
+  STX_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && (done[slot] >> dev) & 1ull) return STX_OK;
+  STX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (dev < 64) done[slot] |= 1ull << dev;
+  return STX_OK;
 }
 
 }  // namespace tc
@@ -1045,8 +1179,11 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   int64_t aoff, coff, total;
   stx_ppo_arena_offsets(actor, critic, &aoff, &coff, &total);
   const int64_t noff[2] = {aoff, coff};
+  const bool fused = g_plan.fused;
+  const int num_tiles = (int)(mb / 128);
+  const int n_fb = fused ? g_plan.fb : kCtaPerNet;  // K3a CTAs per network
 
-  // ---- K3a ----
+  // ---- K3a parameters ----
   FbParams fp{};
   CUtensorMap tmW0[2], tmW1[2];
   for (int n = 0; n < 2; ++n) {
@@ -1061,7 +1198,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     fn.b0 = m->params + (int64_t)D * kH, fn.b1 = m->params + off_w1 + (int64_t)kH * kH, fn.b2 = m->params + off_w2 + (int64_t)kH * A;
     fn.h1 = ws.h1[n], fn.h2 = ws.h2[n], fn.dh1 = ws.dh1[n], fn.dh2 = ws.dh2[n], fn.dz = ws.dz[n];
     fn.db_part = ws.db_part[n], fn.A = A, fn.is_actor = (n == 0);
-    fp.n_cta[n] = kCtaPerNet;
+    fp.n_cta[n] = n_fb;
   }
   fp.obs = reinterpret_cast<const __nv_bfloat16*>(b->obs);
   fp.xg = ws.xg;
@@ -1071,44 +1208,62 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   fp.adv_stats = h->standardize_advantages ? b->adv_stats : nullptr;
   fp.metric_part = ws.metric_part;
   fp.D = D, fp.mb = (int)mb, fp.clip_eps = h->clip_eps, fp.ent_coef = h->ent_coef, fp.vf_coef = h->vf_coef;
+  if (fused) fp.flag_a = ws.flags, fp.flag_b = ws.flags + 2 * num_tiles, fp.flag_x = ws.flags + 4 * num_tiles;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    STX_CUDA_OK(cudaFuncSetAttribute(tc_ppo_fwd_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbSmemBytes));
-    STX_CUDA_OK(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
-    attr_set = true;
-  }
-  // 8 epilogue warps: 16 (two parts per step, 80 registers) measured 5 % slower (profiles/README.md)
-  STX_CUDA_OK(launch_pdl(tc_ppo_fwd_bwd_kernel<8>, dim3(2 * kCtaPerNet), dim3(fb_threads(8)), kFbSmemBytes, st, tmW0[0], tmW1[0], tmW0[1],
-                         tmW1[1], fp));
-  STX_LAUNCH_OK();
-
-  // ---- K3b ----
+  // ---- K3b parameters ----
   DwMaps maps;
   DwParams dp{};
-  int cta = 0, jn = 0;
+  int cta = 0, jn = 0, mi = 0;
   const int chunks = (int)(mb / 64);
+  const uint64_t tiles = (uint64_t)num_tiles;
+  int n_w1 = 0, n_w2 = 0, n_w0 = 0;  // partials per network of each weight gradient (for the reduce below)
   for (int n = 0; n < 2; ++n) {
-    const uint64_t tiles = (uint64_t)(mb / 128);
-    // dW1 = h1^T dh2
-    if (int rc = make_map_tiled(&maps.a[jn], ws.h1[n], tiles, 32)) return rc;
-    if (int rc = make_map_tiled(&maps.b[jn], ws.dh2[n], tiles, 32)) return rc;
-    dp.job[jn] = DwJob{ws.part_w1[n], 256, cta, kDwCtaW1, chunks, nullptr};
-    cta += kDwCtaW1, ++jn;
-    // dW2 = h2^T dz
-    if (int rc = make_map_tiled(&maps.a[jn], ws.h2[n], tiles, 32)) return rc;
-    if (int rc = make_map_tiled(&maps.b[jn], ws.dz[n], tiles, 2)) return rc;
-    dp.job[jn] = DwJob{ws.part_w2[n], 16, cta, kDwCtaW2, chunks, nullptr};
-    cta += kDwCtaW2, ++jn;
-    // dW0^T = dh1^T x
-    if (int rc = make_map_tiled(&maps.a[jn], ws.dh1[n], tiles, 32)) return rc;
-    if (int rc = make_map_tiled(&maps.b[jn], ws.xg, tiles, 8)) return rc;
-    dp.job[jn] = DwJob{ws.part_w0[n], 64, cta, kDwCtaW0, chunks, ws.db0_part[n]};  // + db0 = dh1^T * 1
-    cta += kDwCtaW0, ++jn;
+    // tensor-map pairs of this network: m1 (h1, dh2) -> dW1, m2 (h2, dz) -> dW2, m0 (dh1, xg) -> dW0^T (+ db0 = dh1^T * 1)
+    const int m1 = mi++, m2 = mi++, m0 = mi++;
+    if (int rc = make_map_tiled(&maps.a[m1], ws.h1[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[m1], ws.dh2[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.a[m2], ws.h2[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[m2], ws.dz[n], tiles, 2)) return rc;
+    if (int rc = make_map_tiled(&maps.a[m0], ws.dh1[n], tiles, 32)) return rc;
+    if (int rc = make_map_tiled(&maps.b[m0], ws.xg, tiles, 8)) return rc;
+    const DwSub s1{ws.part_w1[n], nullptr, 256, m1, 0, 0};
+    const DwSub s2{ws.part_w2[n], nullptr, 16, m2, fused ? 96 : 0, 0};
+    const DwSub s0{ws.part_w0[n], ws.db0_part[n], 64, m0, 0, 1};
+    auto add_job = [&](int n_cta, int n_sub, DwSub a, DwSub c) {
+      DwJob& j = dp.job[jn++];
+      j.sub[0] = a, j.sub[1] = c, j.n_sub = n_sub, j.cta_begin = cta, j.n_cta = n_cta, j.num_chunks = chunks, j.net = n;
+      cta += n_cta;
+    };
+    if (fused) {
+      add_job(g_plan.fw1, 1, s1, s1);
+      add_job(g_plan.fw02, 2, s2, s0);  // per chunk: dW2 (operands complete after E3) first, then dW0 (needs dh1)
+      n_w1 = g_plan.fw1, n_w2 = n_w0 = g_plan.fw02;
+    } else {
+      add_job(kDwCtaW1, 1, s1, s1);
+      add_job(kDwCtaW2, 1, s2, s2);
+      add_job(kDwCtaW0, 1, s0, s0);
+      n_w1 = kDwCtaW1, n_w2 = kDwCtaW2, n_w0 = kDwCtaW0;
+    }
   }
-  dp.n_jobs = jn;
-  STX_CUDA_OK(launch_pdl(tc_dw_kernel, dim3(cta), dim3(kDwThreads), kDwSmemBytes, st, maps, dp));
-  STX_LAUNCH_OK();
+  dp.n_jobs = jn, dp.num_tiles = num_tiles;
+  if (fused) dp.flag_a = fp.flag_a, dp.flag_b = fp.flag_b, dp.flag_x = fp.flag_x;
+
+  // ---- launches ----
+  // 8 epilogue warps: 16 (two parts per step, 80 registers) measured 5 % slower (profiles/README.md)
+  if (fused) {
+    if (int rc = opt_in_smem(tc_ppo_fused_kernel<8>, kFbSmemBytes > kDwSmemBytes ? kFbSmemBytes : kDwSmemBytes, 2)) return rc;
+    STX_CUDA_OK(launch_pdl(tc_ppo_fused_kernel<8>, dim3(2 * n_fb + cta), dim3(fb_threads(8)),
+                           kFbSmemBytes > kDwSmemBytes ? kFbSmemBytes : kDwSmemBytes, st, tmW0[0], tmW1[0], tmW0[1], tmW1[1], fp, maps, dp));
+    STX_LAUNCH_OK();
+  } else {
+    if (int rc = opt_in_smem(tc_ppo_fwd_bwd_kernel<8>, kFbSmemBytes, 0)) return rc;
+    if (int rc = opt_in_smem(tc_dw_kernel, kDwSmemBytes, 1)) return rc;
+    STX_CUDA_OK(launch_pdl(tc_ppo_fwd_bwd_kernel<8>, dim3(2 * n_fb), dim3(fb_threads(8)), kFbSmemBytes, st, tmW0[0], tmW1[0], tmW0[1],
+                           tmW1[1], fp));
+    STX_LAUNCH_OK();
+    STX_CUDA_OK(launch_pdl(tc_dw_kernel, dim3(cta), dim3(kDwThreads), kDwSmemBytes, st, maps, dp));
+    STX_LAUNCH_OK();
+  }
 
   // ---- reduce ----
   RedParams rp{};
@@ -1127,17 +1282,18 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
     const int A = nets[n]->sizes[3];
     const int64_t o_w0 = noff[n], o_b0 = o_w0 + (int64_t)D * kH, o_w1 = o_b0 + kH, o_b1 = o_w1 + (int64_t)kH * kH, o_w2 = o_b1 + kH,
                   o_b2 = o_w2 + (int64_t)kH * A;
-    add_seg(ws.part_w1[n], 65536, kDwCtaW1, kH, kH, 256, 0, kH, o_w1, n, 1);           // dW1[in][out]
-    add_seg(ws.part_w0[n], 256 * 64, kDwCtaW0, kH, D, 64, 1, kH, o_w0, n, 1);          // part(j, d) -> W0[d][j]
-    add_seg(ws.part_w2[n], 256 * 16, kDwCtaW2, kH, A, 16, 0, A, o_w2, n, 1);           // dW2[j][a]
-    add_seg(ws.db0_part[n], 256, kDwCtaW0, 1, kH, 256, 0, kH, o_b0, n, 0);             // db0 from K3b (column sums of dh1)
-    add_seg(ws.db_part[n] + 256, 528, kCtaPerNet, 1, kH, 528, 0, kH, o_b1, n, 0);
-    add_seg(ws.db_part[n] + 512, 528, kCtaPerNet, 1, A, 528, 0, A, o_b2, n, 0);
+    add_seg(ws.part_w1[n], 65536, n_w1, kH, kH, 256, 0, kH, o_w1, n, 1);           // dW1[in][out]
+    add_seg(ws.part_w0[n], 256 * 64, n_w0, kH, D, 64, 1, kH, o_w0, n, 1);          // part(j, d) -> W0[d][j]
+    add_seg(ws.part_w2[n], 256 * 16, n_w2, kH, A, 16, 0, A, o_w2, n, 1);           // dW2[j][a]
+    add_seg(ws.db0_part[n], 256, n_w0, 1, kH, 256, 0, kH, o_b0, n, 0);             // db0 from K3b (column sums of dh1)
+    add_seg(ws.db_part[n] + 256, 528, n_fb, 1, kH, 528, 0, kH, o_b1, n, 0);
+    add_seg(ws.db_part[n] + 512, 528, n_fb, 1, A, 528, 0, A, o_b2, n, 0);
   }
   rp.n_seg = sidx;
-  rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * kCtaPerNet, rp.metrics = metrics;
+  rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * n_fb, rp.metrics = metrics;
   rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
   rp.overwrite = opt ? 1 : h->overwrite_grads;
+  if (fused) rp.flags = ws.flags, rp.n_flags = 5 * num_tiles;
   // side output for the fused optimiser: partials[seg][block] right after the 16-byte header of its scratch
   void* adam_scratch = opt ? opt->scratch : h->adam_scratch;
   rp.sumsq = (rp.overwrite && adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(adam_scratch) + 16) : nullptr;

@@ -23,26 +23,9 @@ class CartPoleEnv(Environment):
 
     def __init__(self, device="cuda", seed: int = 0):
         self.device = torch.device(device)
-        self._seed = int(seed)
-        self._gen = None  # dedicated generator: reset states are a function of the seed, not of torch's global stream
-
-    @property
-    def seed(self) -> int:
-        return self._seed
-
-    @seed.setter
-    def seed(self, value: int) -> None:
-        """learner_setup assigns `arch.seed + 7919 * rank + ...` per rank / shard (the reference splits its reset
-        keys per device, batch and env, ff_ppo.py:492-501): re-seeding restarts the reset-state stream."""
-        self._seed = int(value)
-        if self._gen is not None:
-            self._gen.manual_seed(self._seed)
-
-    def _generator(self) -> torch.Generator:
-        if self._gen is None:
-            self._gen = torch.Generator(device=self.device)
-            self._gen.manual_seed(self._seed)
-        return self._gen
+        # learner_setup assigns `arch.seed + 7919 * rank + ...` per rank / shard before reset() (the reference splits its
+        # reset keys per device, batch and env, ff_ppo.py:492-501); reset states are a pure function of (seed, env, draw #)
+        self.seed = int(seed)
 
     def observation_space(self) -> ArraySpace:
         return ArraySpace((4,), torch.float32, self.device)
@@ -50,13 +33,31 @@ class CartPoleEnv(Environment):
     def action_space(self) -> DiscreteSpace:
         return DiscreteSpace(2)
 
-    def _fresh(self, E: int) -> torch.Tensor:
-        return (torch.rand(E, 4, device=self.device, generator=self._generator()) - 0.5) * 0.1
+    _M32 = 0xFFFFFFFF
+
+    def _fresh(self, E: int, ctr: torch.Tensor, seed: int) -> torch.Tensor:
+        """U(-0.05, 0.05) reset states from a counter-based hash (murmur3 finaliser on 32-bit lanes held in int64) of
+        (seed, env, component, draw counter).  Stateless: no torch.Generator, so it is CUDA-graph safe (the counter is a
+        device tensor advanced inside the graph) and a run is a function of arch.seed."""
+        M = self._M32
+        idx = torch.arange(E * 4, dtype=torch.int64, device=self.device).view(E, 4)
+        mix = ((seed & M) * 0x27D4EB2F + ((seed >> 32) & M) * 0x165667B1 + 0x9E3779B9) & M
+        h = (idx * 0x9E3779B1 + ctr * 0x85EBCA77 + mix) & M
+        h = h ^ (h >> 16)
+        h = (h * 0x85EBCA6B) & M
+        h = h ^ (h >> 13)
+        h = (h * 0xC2B2AE35) & M
+        h = h ^ (h >> 16)
+        u = (h >> 8).to(torch.float32) * (1.0 / 16777216.0)
+        return (u - 0.5) * 0.1
 
     def reset(self, keys) -> Tuple[Dict[str, Any], TimeStep]:
         E, dev = len(keys), self.device
-        phys = self._fresh(E)
-        state = {"phys": phys, "time": torch.zeros(E, dtype=torch.int32, device=dev),
+        seed = int(self.seed)
+        ctr = torch.zeros((), dtype=torch.int64, device=dev)
+        phys = self._fresh(E, ctr, seed)
+        ctr += 1
+        state = {"phys": phys, "reset_ctr": ctr, "seed": seed, "time": torch.zeros(E, dtype=torch.int32, device=dev),
                  "run_return": torch.zeros(E, device=dev), "run_length": torch.zeros(E, dtype=torch.int32, device=dev)}
         ts = TimeStep(torch.full((E,), StepType.FIRST, dtype=torch.int8, device=dev), torch.zeros(E, device=dev),
                       torch.ones(E, device=dev), phys.clone(),
@@ -92,7 +93,8 @@ class CartPoleEnv(Environment):
         ret = state["run_return"] + 1.0
         ln = state["run_length"] + 1
         out.next_obs.copy_(nxt)
-        new_phys = torch.where(last[:, None], self._fresh(nxt.shape[0]), nxt)
+        new_phys = torch.where(last[:, None], self._fresh(nxt.shape[0], state["reset_ctr"], state["seed"]), nxt)
+        state["reset_ctr"] += 1
         out.obs.copy_(new_phys)
         out.reward.fill_(1.0)
         out.done.copy_(term)

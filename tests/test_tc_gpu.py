@@ -159,12 +159,12 @@ def test_learner_bf16_update_tracks_bf16_oracle(E, T, nmb):
     cores, bf16 weight shadows refreshed by the fused Adam) vs the oracle run with the same bf16 operand
     rounding, actions and permutations injected.
 
-    Bounds.  Adam's first / second moments are linear / quadratic in the gradients, so they are compared
-    norm-wise at 1e-2 per network after all epochs x minibatches optimiser steps (what is left between the
-    kernels and the oracle is fp32 summation order, fast-math exp/log in the loss epilogue and rare 1-ulp bf16
-    rounding flips of a hidden activation).  The parameter CHANGE is reported and bounded at 5e-2 norm-wise:
-    Adam turns every entry's gradient into a step of ~lr whatever its size, so entries whose (tiny) gradient
-    differs in the last bits move differently."""
+    Bounds.  This is the integration check of the whole graph-captured step: GAE targets tight (1e-4), loss metrics
+    2e-2, optimiser counters exact, bf16 shadow == rounded master.  The END STATE of 4 x nmb chained Adam steps is
+    compared loosely (first moments 0.15, second moments 0.05, parameter change 0.15 norm-wise; measured 0.03-0.06 /
+    0.01-0.02): both sides' per-step gradients agree to ~1e-4 (scripts/diag_bf16_steps.py, and the per-step test below
+    holds them to 5e-3), but Adam turns every entry's gradient into a step of ~lr whatever its size, so entries whose
+    (tiny) gradient differs in the last bits move apart and the two parameter trajectories drift from each other."""
     from stoix_b200 import ops, random as srandom
     from stoix_b200.config import compose
     from stoix_b200.systems.ppo.anakin import ff_ppo
@@ -220,14 +220,100 @@ def test_learner_bf16_update_tracks_bf16_oracle(E, T, nmb):
     ra, rc = _rel(da, a2.flat() - p0a), _rel(dc, c2.flat() - p0c)
     print(f"E={E} T={T}: after {4 * nmb} Adam steps, bf16 kernels vs bf16 oracle: " + ", ".join(f"{k} rel {v:.2e}" for k, v in errs.items())
           + f"; parameter change actor rel {ra:.3e}, critic rel {rc:.3e}")
+    # end state of a whole update: trajectory divergence under Adam's per-entry normalisation dominates (see the docstring;
+    # the per-step gradients are held to 5e-3 by test_learner_bf16_per_step_gradients_match_oracle)
     for k, v in errs.items():
-        assert v < 1e-2, f"{k}: norm-wise relative error {v:.3e} of the Adam moment after {4 * nmb} steps"
-    assert ra < 5e-2 and rc < 5e-2, (ra, rc)
+        assert v < (0.15 if k.endswith("mu") else 0.05), f"{k}: norm-wise relative error {v:.3e} of the Adam moment after {4 * nmb} steps"
+    assert ra < 0.15 and rc < 0.15, (ra, rc)
     assert a_tree.arena_counts.cpu().tolist() == [4 * nmb] * 4
     shadow = a_tree.arena_bf16
     assert torch.equal(shadow, a_tree.arena.to(torch.bfloat16))
     for name in ("actor_loss", "entropy", "value_loss"):
         np.testing.assert_allclose(f64(out.train_metrics[name][0]), metrics[name], rtol=2e-2, atol=2e-3)
+
+
+def _per_step_gradient_errors(E, T, nmb, check_steps, perturb=0.05):
+    """Runs the bf16 learner's rollout + GAE, then the update's epochs x minibatches by hand through the C ABI
+    (stx_ppo_minibatch_grads + stx_clip_adam_step, the calls the learner makes); at every step in `check_steps` the
+    oracle evaluates the gradient FROM THE KERNELS' CURRENT PARAMETERS with the same bf16 operand rounding, so each
+    optimiser step is compared on its own (no trajectory drift).  Returns {step: (actor rel err, critic rel err)}."""
+    from stoix_b200 import ops, random as srandom
+    from stoix_b200.config import compose
+    from stoix_b200.systems.ppo.anakin import ff_ppo
+    from stoix_b200.utils import make_env
+    from stoix_b200.utils.total_timestep_checker import check_total_timesteps
+
+    cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E}", f"system.rollout_length={T}",
+                                     f"system.num_minibatches={nmb}", f"arch.total_timesteps={E * T * 2}", "arch.num_evaluation=1",
+                                     "arch.precision=bf16", "logger.use_console=False", "arch.cuda_graph=False"])
+    cfg.num_devices, cfg.rank = 1, 0
+    cfg = check_total_timesteps(cfg, quiet=True)
+    env, _ = make_env.make(cfg)
+    keys = srandom.split(srandom.PRNGKey(0), 4)
+    learn, _, state = ff_ppo.learner_setup(env, (keys[0], keys[2], keys[3]), cfg)
+    a_tree, c_tree = state.params.actor_params, state.params.critic_params
+    with torch.no_grad():
+        g = torch.Generator(device="cuda").manual_seed(1)
+        a_tree.arena.add_(torch.randn(a_tree.arena.shape, device="cuda", generator=g) * perturb)
+        ops.cast_bf16(a_tree.arena, out=a_tree.arena_bf16)
+    learn.ensure_built(state)
+    b = learn.built
+    learn.phases["rollout"](state)
+    learn.phases["gae"](state)
+    torch.cuda.synchronize()
+    sh, sa, sc = b["shards"][0], b["sa"], b["sc"]
+    _, coff, total = ops.arena_offsets(sa, sc)
+    D, B = sa.sizes[0], T * E
+    mb = B // nmb
+    f64 = lambda t: t.detach().float().cpu().numpy().astype(np.float64)
+    obs, act = f64(sh.obs[:T]).reshape(B, D), sh.action.cpu().numpy().reshape(B)
+    lp_old, v_old, tgt = f64(sh.log_prob).reshape(B), f64(sh.value).reshape(B), f64(sh.targets).reshape(B)
+    adv = O.standardize(f64(sh.advantages)).reshape(B)
+    batch = ops.PpoBatch(sh.obs[:T].view(B, D), sh.action.view(B), sh.log_prob.view(B), sh.value.view(B), sh.advantages.view(B),
+                         sh.targets.view(B), sh.adv_stats, None)
+    grads, metrics = torch.zeros(total, device="cuda"), torch.zeros(8, device="cuda")
+    rng = np.random.default_rng(0)
+    out, step = {}, 0
+    for ep in range(4):
+        perm = rng.permutation(B).astype(np.int32)
+        batch.perm = torch.as_tensor(perm, device="cuda")
+        for i in range(nmb):
+            if step in check_steps:
+                actor = O.MLPParams.from_flat(f64(a_tree.flat), list(sa.sizes)).astype(np.float32)
+                critic = O.MLPParams.from_flat(f64(c_tree.flat), list(sc.sizes)).astype(np.float32)
+            ops.ppo_minibatch_grads(sa, sc, b["arena"], batch, i * mb, mb, 0.2, 0.01, 0.5, True, grads, metrics, b["ws"],
+                                    ops.STX_PREC_BF16, 1.0, b["arena_bf16"], overwrite=True)
+            if step in check_steps:
+                idx = perm[i * mb:(i + 1) * mb]
+                gk = f64(grads)
+                lg, a_acts = O.mlp_forward(actor, obs[idx], bf16_operands=True)
+                _, dlg, _ = O.actor_loss_and_dlogits(lg.astype(np.float64), act[idx], lp_old[idx], adv[idx], 0.2, 0.01)
+                ga = O.mlp_backward(actor, a_acts, dlg, bf16_operands=True).flat()
+                v, c_acts = O.mlp_forward(critic, obs[idx], bf16_operands=True)
+                _, dv, _ = O.critic_loss_and_dvalue(v[:, 0].astype(np.float64), v_old[idx], tgt[idx], 0.2, 0.5)
+                gc = O.mlp_backward(critic, c_acts, dv[:, None], bf16_operands=True).flat()
+                out[step] = (_rel(gk[:sa.param_count], ga), _rel(gk[coff:coff + sc.param_count], gc))
+            ops.clip_adam_step(b["plan"], b["arena"], grads, a_tree.arena_mu, a_tree.arena_nu, params_bf16=b["arena_bf16"])
+            step += 1
+    torch.cuda.synchronize()
+    assert a_tree.arena_counts.cpu().tolist() == [4 * nmb] * 4
+    return out
+
+
+@pytest.mark.parametrize("E,T,nmb,check_steps", [
+    (128, 16, 4, tuple(range(16))),
+    (4096, 128, 16, (0, 1, 15, 16, 31, 47, 63)),   # BASELINE config 2; the oracle costs ~1 s per checked step
+])
+def test_learner_bf16_per_step_gradients_match_oracle(E, T, nmb, check_steps):
+    """Every checked optimiser step of a real update (real rollout values, GAE targets, standardised advantages, the
+    parameters Adam has produced so far): gradient of both losses vs the bf16-rounding oracle, norm-wise 5e-3 per
+    network (measured ~1e-4; the layer-0 bias gradient alone sits at ~1.5e-3: it is summed from bf16-rounded dh1)."""
+    errs = _per_step_gradient_errors(E, T, nmb, set(check_steps))
+    for st in sorted(errs):
+        print(f"E={E} T={T} step {st:2d}: actor rel {errs[st][0]:.2e}  critic rel {errs[st][1]:.2e}")
+    assert sorted(errs) == sorted(check_steps)
+    for st, (ra, rc) in errs.items():
+        assert ra < 5e-3 and rc < 5e-3, f"step {st}: actor {ra:.3e} critic {rc:.3e}"
 
 
 def test_fused_rollout_is_bit_identical_to_per_step_path():
