@@ -143,6 +143,9 @@ int stx_tc_debug_forward(const StxMlp* mlp, const void* x, int64_t ldx, int64_t 
 /* Profiling hook: device buffer of >= 32 int64 that K3a's CTA 0 fills with clock64() stamps of its second
  * tile (MMA-warp slots 0..9, first epilogue warp slots 16..27); NULL disables.  Synchronous (not for capture). */
 int stx_tc_debug_set_clock_buffer(long long* buf);
+/* Profiling hook of the fused K3 launch: device buffer of [148][8] int64 filled per CTA with
+ * {role, total cycles, wait/stall breakdown ...} (see stx_tc_ppo.cu g_prof_buf); NULL disables. */
+int stx_tc_debug_set_prof_buffer(long long* buf);
 
 /* Categorical head ops on logits (E, A) -- tfd.Categorical (stoix/networks/heads.py:41) as used at
  * ff_ppo.py:100-101.  If sample != 0: action = argmax_j(logits_j + Gumbel_j) with Philox4x32-10
@@ -286,6 +289,24 @@ int stx_tc_rollout_synth(const StxMlp* actor, void* obs, void* next_obs, int32_t
                          uint64_t env_seed, uint64_t env_step, const uint64_t* env_counter, float p_term,
                          float p_trunc, uint64_t cat_seed, uint64_t cat_offset, const uint64_t* cat_counter,
                          void* stream);
+
+/* ---- Observation normalisation (stoix/utils/running_statistics.py) -------------------------------------------
+ * Replaces update_statistics (running_statistics.py:204-345: batched Welford, psum over the mapped axes) and normalize
+ * (:348-363) on the ff_ppo call sites stoix/systems/ppo/anakin/ff_ppo.py:90-94, 113-115, 145-162.
+ *   accumulate: one pass over the raw fp32 batch x[rows][D] (optional per-row weights): sums[0..D) = sum w (x - mean),
+ *               sums[D..2D) = sum w (x - mean)^2, sums[2D] = sum w, in double (deterministic two-level reduction).
+ *               With N ranks the caller all-reduces (SUM) the 2D+1 doubles -- the reference's two psums in one exchange.
+ *   finalize:   count += W; delta = S1 / count; mean += delta; summed_variance += S2 - delta * S1;
+ *               std = clip(sqrt(clip(max(sv, 0) / count, min^2, max^2)), min, max)          -- in place on the state.
+ *   normalize:  out = (x - mean) / std, optional clip to [-max_abs_value, max_abs_value] (<= 0: none); out fp32 or bf16.
+ * D <= 256.  scratch: stx_running_stats_scratch_bytes(D) bytes, zero-initialised once by the caller. */
+size_t stx_running_stats_scratch_bytes(int D);
+int stx_running_stats_accumulate(const float* x, const float* weights, int64_t rows, int D, const float* mean, double* sums,
+                                 void* scratch, void* stream);
+int stx_running_stats_finalize(const double* sums, int D, int64_t* count, float* mean, float* summed_variance, float* std,
+                               float std_min_value, float std_max_value, void* stream);
+int stx_obs_normalize(const float* x, int64_t rows, int D, const float* mean, const float* std, float max_abs_value, void* out,
+                      int out_bf16, void* stream);
 
 /* Utility casts used by the bf16 path (obs / weight shadows). */
 int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -48,6 +48,11 @@ __device__ long long* g_clock_buf = nullptr;
     if (clk_buf != nullptr && (cond)) clk_buf[slot] = clock64();   \
   } while (0)
 #define STX_STAMP(slot) STX_STAMP_AT(slot, it == 1 && lane == 0)
+// optional per-CTA cycle accounting of the fused launch (scripts/profile_k3_fused.py): [gridDim][8] long long
+//   K3a CTAs: 0 role id (1), 1 total, 2 cycles inside flag_signal (epilogue warp 5), 3 tiles
+//   dW CTAs:  0 role id (2 + job), 1 total, 2 TMA thread waiting for flags, 3 TMA thread waiting for a free stage,
+//             4 MMA thread waiting for a full stage, 5 pipeline iterations
+__device__ long long* g_prof_buf = nullptr;
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;
@@ -104,6 +109,11 @@ __device__ __forceinline__ void flag_signal(uint32_t* f, int lane) {
     __threadfence();
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
   }
+}
+__device__ __forceinline__ void flag_signal_timed(uint32_t* f, int lane, long long& acc) {
+  const long long t0 = clock64();
+  flag_signal(f, lane);
+  acc += clock64() - t0;
 }
 // Consumer side (one thread): spin until `want` arrivals, then order the async-proxy (TMA) reads that follow behind it.
 __device__ __forceinline__ void flag_wait(const uint32_t* f, uint32_t want, const char* what) {
@@ -191,6 +201,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
   // align by OFFSET (not through an integer cast) so that the compiler keeps the shared address space: LDS/STS, not generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
+  const long long prof_t0 = clock64();
   long long* const clk_buf = blockIdx.x == 0 ? g_clock_buf : nullptr;  // one load; the stamps themselves stay cheap
   STX_STAMP_AT(56, threadIdx.x == 0);
   float* s_b0 = reinterpret_cast<float*>(smem + kOffBias);
@@ -439,6 +450,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
     // burst, the later stores of a warp block it behind the other warps' bursts; so the four 512-byte stores of a chunk
     // are issued one at a time between the four column groups of the NEXT chunk this warp processes (whatever phase
     // that chunk belongs to), where the store path has long drained.
+    long long prof_sig = 0;
     uint32_t pend[16];
     uint4* pend_ptr = nullptr;
 #pragma unroll
@@ -493,7 +505,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
           // the flushes above issued this warp's last dh1 stores of the PREVIOUS tile: dh1 of that tile is complete
-          if (layer == 0 && cc == 0 && it > 0 && p.flag_b != nullptr) flag_signal(p.flag_b + which * num_tiles + (tile - ncta), lane);
+          if (layer == 0 && cc == 0 && it > 0 && p.flag_b != nullptr) flag_signal_timed(p.flag_b + which * num_tiles + (tile - ncta), lane, prof_sig);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
           pend_ptr = tiled_ptr(hout, mrow, c * 4, 32);
@@ -600,7 +612,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
           // first chunk of E4: the flushes above issued this warp's last dh2 stores; h1, h2 and dz went out earlier
-          if (layer == 0 && cc == 0 && p.flag_a != nullptr) flag_signal(p.flag_a + which * num_tiles + tile, lane);
+          if (layer == 0 && cc == 0 && p.flag_a != nullptr) flag_signal_timed(p.flag_a + which * num_tiles + tile, lane, prof_sig);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
           pend_ptr = tiled_ptr(dout, mrow, c * 4, 32);
@@ -615,9 +627,13 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) STX_FLUSH_PENDING(g);  // the last chunk of the last tile
-    if (my_tiles > 0 && p.flag_b != nullptr) flag_signal(p.flag_b + which * num_tiles + cta_in_net + (my_tiles - 1) * ncta, lane);
+    if (my_tiles > 0 && p.flag_b != nullptr) flag_signal_timed(p.flag_b + which * num_tiles + cta_in_net + (my_tiles - 1) * ncta, lane, prof_sig);
 #undef STX_FLUSH_PENDING
     STX_STAMP_AT(61, warp == 5 && lane == 0);
+    if (g_prof_buf != nullptr && warp == 5 && lane == 0) {
+      long long* pb = g_prof_buf + (int64_t)blockIdx.x * 8;
+      pb[0] = 1, pb[1] = clock64() - prof_t0, pb[2] = prof_sig, pb[3] = my_tiles;
+    }
   }
   // ---- teardown: bias-gradient and metric partials of this CTA ----
   tc_fence_before();
@@ -710,6 +726,8 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
   uint64_t* acc_done = bars + 2 * kDwStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDwStages + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long prof_t0 = clock64();
+  long long* const prof = g_prof_buf ? g_prof_buf + (int64_t)blockIdx.x * 8 : nullptr;
 
   int j = 0;
   while (j + 1 < p.n_jobs && cta_abs >= p.job[j + 1].cta_begin) ++j;
@@ -748,6 +766,7 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
   if (warp == 0) {
     if (elect_one()) {
       const uint64_t pol_stream = l2_evict_first();  // every activation tile is read exactly once
+      long long w_flag = 0, w_empty = 0;
       int k = 0;
       for (int it = 0; it < my_chunks; ++it) {
         // split launches: newest rows first (K3a wrote the last tiles most recently, so they are the likeliest L2 residents);
@@ -758,7 +777,9 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
         for (int sj = 0; sj < n_sub; ++sj, ++k) {
           const DwSub& sub = job.sub[sj];
           const int s = k % kDwStages;
+          long long tq = clock64();
           if (k >= kDwStages) mbar_wait(&empty[s], ((k / kDwStages) & 1) ^ 1, 20);
+          w_empty += clock64() - tq, tq = clock64();
           if (fused) {
             flag_wait(p.flag_a + job.net * p.num_tiles + tile, kFlagEpi, "K3 activations (h1, h2, dz, dh2) of a tile");
             if (sub.wait_b) {
@@ -766,6 +787,7 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
               flag_wait(p.flag_x + tile, kFlagGather, "K3 gathered input rows of a tile");
             }
           }
+          w_flag += clock64() - tq;
           uint8_t* st = smem + s * kDwStageBytes;
           mbar_arrive_expect_tx(&full[s], 32768 + (uint32_t)sub.N * 128);
           // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
@@ -773,9 +795,11 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
           tma_load_2d_hint(st + 32768, &maps.b[sub.map], &full[s], r0 * 2, tile * (sub.N >> 3), pol_stream);
         }
       }
+      if (prof) prof[0] = 2 + j, prof[2] = w_flag, prof[3] = w_empty, prof[5] = my_iters;
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_ones = idesc_bf16(128, 16, 1, 1);
+    long long w_full = 0;
     int k = 0;
     for (int it = 0; it < my_chunks; ++it) {
       for (int sj = 0; sj < n_sub; ++sj, ++k) {
@@ -783,7 +807,9 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
         const uint32_t idesc = idesc_bf16(128, sub.N, 1, 1);  // both operands MN-major
         const bool colsum = sub.colsum != nullptr;
         const int s = k % kDwStages;
+        const long long tq = clock64();
         mbar_wait(&full[s], (k / kDwStages) & 1, 21);
+        w_full += clock64() - tq;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a0 = sbase + s * kDwStageBytes, b0 = a0 + 32768;
@@ -808,6 +834,7 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
     }
     if (elect_one()) mma_commit(acc_done);
     __syncwarp();
+    if (prof && lane == 0) prof[4] = w_full;
   } else if (warp < 6) {
     const int q = warp & 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -851,6 +878,7 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
   }
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) prof[1] = clock64() - prof_t0;
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -1087,14 +1115,19 @@ struct TcWs {
 
 constexpr int kCtaPerNet = kNumSMs / 2;              // 74
 // Launch plan, per network (x 2 networks = 148 CTAs).
-//  split (STX_K3_FUSED=0): K3a on 74 CTAs, then K3b with 35/18/21 split-K CTAs for dW1 / dW2 / dW0 -- proportional to the
+//  split (default): K3a on 74 CTAs, then K3b with 35/18/21 split-K CTAs for dW1 / dW2 / dW0 -- proportional to the
 //    bytes each job streams (dW1: h1 + dh2, dW2: h2 + dz, dW0: dh1 + x): K3b alone is HBM-bound, so the CTAs should finish together.
-//  fused (default): ONE launch; 64 K3a CTAs (256 tiles of the benchmark minibatch = exactly 4 each), 6 CTAs accumulate dW1
-//    (tensor-bound: 2048 MMA cycles per tile) and 4 CTAs dW2 + dW0 + db0 (two GEMMs per chunk, 148 KB per tile).
+//  fused (STX_K3_FUSED=1, experimental): ONE launch; 64 K3a CTAs (256 tiles of the benchmark minibatch = exactly 4 each),
+//    6 CTAs accumulate dW1 and 4 CTAs dW2 + dW0 + db0 behind per-tile flags.  Parity-green, but MEASURED SLOWER on B200
+//    (profiles/r02_k3_fused_accounting.txt: 267 us per minibatch step at 64/6/4, 131 us at 40/21/13, split 113 us in the
+//    same eager loop): with the full-size activation workspace the stream still goes through HBM (145 MB written + 145 MB
+//    read per step), and a weight-gradient CTA with 192 KB of TMA loads in flight sustains only ~44 B/clk against that
+//    saturated memory system (1.45k cycles per 64 KB stage against 1.0k of MMA; the 33-40 KB stages of the dW2/dW0 job are
+//    pure latency: 1.6k cycles each).  It needs an L2-resident ring of tile slots to pay off; kept for that experiment.
 //  Tuning switches: STX_DW_SPLIT="w1,w2,w0" (split), STX_K3_SPLIT="fb,w1,w02" (fused), each summing to 74.
 struct K3Plan {
   int w1 = 35, w2 = 18, w0 = 21;   // split
-  bool fused = true;
+  bool fused = false;
   int fb = 64, fw1 = 6, fw02 = 4;  // fused
   K3Plan() {
     int a, b, c;
@@ -1103,7 +1136,7 @@ struct K3Plan {
     e = getenv("STX_K3_SPLIT");
     if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0 && a + b + c == kCtaPerNet) fb = a, fw1 = b, fw02 = c;
     e = getenv("STX_K3_FUSED");
-    if (e && e[0] == '0') fused = false;
+    if (e) fused = e[0] == '1';
   }
 };
 static const K3Plan g_plan;
@@ -1325,6 +1358,11 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
 }
 
 }  // namespace stx
+
+extern "C" int stx_tc_debug_set_prof_buffer(long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(stx::tc::g_prof_buf, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 extern "C" int stx_tc_debug_set_clock_buffer(long long* buf) {
   cudaError_t e = cudaMemcpyToSymbol(stx::tc::g_clock_buf, &buf, sizeof(buf));

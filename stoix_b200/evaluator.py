@@ -25,7 +25,10 @@ def get_ff_evaluator_fn(env, act_fn: Callable, config, eval_multiplier: int = 1)
     n_episodes = int(config.arch.num_eval_episodes) * eval_multiplier
     max_steps = int(config.arch.get("max_eval_steps", 2000))
 
-    def evaluator(params, key) -> Dict[str, torch.Tensor]:
+    def evaluator(params, key, running_statistics=None) -> Dict[str, torch.Tensor]:
+        """running_statistics: normalise the observations like the learner does (stoix/evaluator.py:114-129)."""
+        from .utils.running_statistics import normalize
+
         keys = srandom.split(key, n_episodes + 1)
         state, ts = env.reset(keys[:n_episodes])
         dev = ts.observation.device
@@ -33,7 +36,8 @@ def get_ff_evaluator_fn(env, act_fn: Callable, config, eval_multiplier: int = 1)
         ret = torch.zeros(n_episodes, device=dev)
         length = torch.zeros(n_episodes, dtype=torch.int32, device=dev)
         for step in range(max_steps):
-            action = act_fn(params, ts.observation, keys[-1] + step)
+            observation = ts.observation if running_statistics is None else normalize(ts.observation, running_statistics)
+            action = act_fn(params, observation, keys[-1] + step)
             state, ts = env.step(state, action)
             ret += ts.reward * alive
             length += alive.to(torch.int32)

@@ -85,6 +85,9 @@ class _FeedForward:
         obs = self.input_layer(observation)
         lead = obs.shape[:-1]
         x = obs.reshape(-1, obs.shape[-1])
+        want = torch.bfloat16 if self.precision == ops.STX_PREC_BF16 else torch.float32
+        if x.dtype != want:  # e.g. fp32 (normalised) observations into the bf16 kernels (cold paths: evaluator, user calls)
+            x = ops.cast_bf16(x.contiguous()) if (want == torch.bfloat16 and x.dtype == torch.float32) else x.to(want)
         if not x.is_contiguous():
             x = x.contiguous()
         out = ops.mlp_forward(params.spec, params.flat, x, precision=self.precision, params_bf16=params.flat_bf16)

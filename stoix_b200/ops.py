@@ -509,3 +509,56 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
         out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     _lib.check(_lib.load().stx_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _stream()), "stx_cast_f32_to_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# observation normalisation (stoix/utils/running_statistics.py)
+# ------------------------------------------------------------------------------------------------
+
+
+def running_stats_accumulate(x: torch.Tensor, mean: torch.Tensor, weights: Optional[torch.Tensor] = None,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sums[2D+1] (float64) = [sum w (x - mean), sum w (x - mean)^2, sum w] over the rows of x (rows, D) float32."""
+    dev = _need_cuda(x, mean, weights, out)
+    D = int(mean.numel())
+    if x.dtype != torch.float32 or mean.dtype != torch.float32 or x.numel() % D != 0:
+        raise StxError("running_stats_accumulate: x must be float32 with a trailing feature dim equal to mean.numel()")
+    rows = x.numel() // D
+    if weights is not None and (weights.dtype != torch.float32 or weights.numel() != rows):
+        raise StxError("running_stats_accumulate: weights must be float32 with one entry per batch row")
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(2 * D + 1, dtype=torch.float64, device=dev)
+    scratch = _zeros_scratch(("rstats", D), lib.stx_running_stats_scratch_bytes(D), dev)
+    _lib.check(lib.stx_running_stats_accumulate(_p(x), _p(weights), rows, D, _p(mean), _p(out), _p(scratch), _stream()),
+               "stx_running_stats_accumulate")
+    return out
+
+
+def running_stats_finalize(sums: torch.Tensor, count: torch.Tensor, mean: torch.Tensor, summed_variance: torch.Tensor,
+                           std: torch.Tensor, std_min_value: float, std_max_value: float) -> None:
+    """In-place Welford update of (count int64[1], mean, summed_variance, std float32[D]) from accumulated sums."""
+    _need_cuda(sums, count, mean, summed_variance, std)
+    D = int(mean.numel())
+    if sums.dtype != torch.float64 or sums.numel() != 2 * D + 1 or count.dtype != torch.int64:
+        raise StxError("running_stats_finalize: sums must be float64[2D+1], count int64[1]")
+    _lib.check(_lib.load().stx_running_stats_finalize(_p(sums), D, _p(count), _p(mean), _p(summed_variance), _p(std),
+                                                      float(std_min_value), float(std_max_value), _stream()),
+               "stx_running_stats_finalize")
+
+
+def obs_normalize(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  out_dtype: torch.dtype = torch.float32, max_abs_value: Optional[float] = None) -> torch.Tensor:
+    """(x - mean) / std over the trailing feature dim (running_statistics.py:348-363); out float32 or bfloat16."""
+    dev = _need_cuda(x, mean, std, out)
+    D = int(mean.numel())
+    if x.dtype != torch.float32 or x.numel() % D != 0:
+        raise StxError("obs_normalize: x must be float32 with a trailing feature dim equal to mean.numel()")
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    if out.dtype not in (torch.float32, torch.bfloat16) or out.numel() != x.numel():
+        raise StxError("obs_normalize: out must be float32 or bfloat16 with x's element count")
+    _lib.check(_lib.load().stx_obs_normalize(_p(x), x.numel() // D, D, _p(mean), _p(std),
+                                             float(max_abs_value) if max_abs_value is not None else 0.0, _p(out),
+                                             int(out.dtype == torch.bfloat16), _stream()), "stx_obs_normalize")
+    return out

@@ -69,10 +69,14 @@ def _world() -> Tuple[int, int]:
 class _Shard:
     """Trajectory buffers of one (device, update-batch) shard: PPOTransition fields, time-major."""
 
-    def __init__(self, T: int, E: int, D: int, A: int, obs_dtype, device):
+    def __init__(self, T: int, E: int, D: int, A: int, obs_dtype, device, normalize: bool = False):
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
         self.obs = z(T + 1, E, D, dt=obs_dtype)      # row t = last_timestep.observation of step t
         self.next_obs = z(T, E, D, dt=obs_dtype)     # timestep.extras["next_obs"]   (ff_ppo.py:113)
+        # normalize_observations: the environment writes RAW fp32 observations here (they feed the running statistics,
+        # ff_ppo.py:145-162) and obs / next_obs above hold the normalised copies every network kernel reads (:90-94,113-115)
+        self.obs_raw = z(T + 1, E, D) if normalize else None
+        self.next_obs_raw = z(T, E, D) if normalize else None
         self.action = z(T, E, dt=torch.int32)
         self.log_prob = z(T, E)
         self.value = z(T, E)
@@ -90,8 +94,14 @@ class _Shard:
         self.adv_stats: Optional[torch.Tensor] = None
 
     def step_out(self, t: int) -> StepOut:
-        return StepOut(self.obs[t + 1], self.next_obs[t], self.reward[t], self.done[t], self.truncated[t],
+        obs, nxt = (self.obs, self.next_obs) if self.obs_raw is None else (self.obs_raw, self.next_obs_raw)
+        return StepOut(obs[t + 1], nxt[t], self.reward[t], self.done[t], self.truncated[t],
                        self.episode_return[t], self.episode_length[t], self.is_terminal_step[t])
+
+    @property
+    def env_obs(self) -> torch.Tensor:
+        """(T+1, E, D) observations as the environment produced them (raw when normalising)."""
+        return self.obs if self.obs_raw is None else self.obs_raw
 
     def transition(self, T: int) -> PPOTransition:
         info = {"episode_return": self.episode_return, "episode_length": self.episode_length,
@@ -137,7 +147,8 @@ def get_learner_fn(
         _, coff, total = ops.arena_offsets(sa, sc)
         D, A = sa.sizes[0], sa.sizes[-1]
         obs_dtype = torch.bfloat16 if precision == ops.STX_PREC_BF16 else torch.float32
-        shards = [_Shard(T, E, D, A, obs_dtype, dev) for _ in range(U)]
+        rs = getattr(state, "running_statistics", None)
+        shards = [_Shard(T, E, D, A, obs_dtype, dev, normalize=rs is not None) for _ in range(U)]
         decay = bool(sysc.decay_learning_rates)
         plan = ops.AdamPlan(
             [(0, sa.param_count, actor_opt.init_lr, actor_opt.max_grad_norm),
@@ -166,6 +177,7 @@ def get_learner_fn(
             roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # categorical call index
             perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # shuffle stream index
             side_stream=torch.cuda.Stream(device=dev),                # the shuffles run here, underneath the rollout
+            rs=rs, rs_sums=torch.zeros(2 * D + 1, dtype=torch.float64, device=dev) if rs is not None else None,
             graph=None, eager_done=False,
         )
 
@@ -174,6 +186,8 @@ def get_learner_fn(
         b = built
         sh: _Shard = b["shards"][u]
         a_tree = state.params.actor_params
+        if b["rs"] is not None:  # normalise the observation with the PRE-update statistics (ff_ppo.py:90-94)
+            ops.obs_normalize(sh.obs_raw[t], b["rs"].mean, b["rs"].std, out=sh.obs[t])
         # SELECT ACTION (ff_ppo.py:97-101): logits -> sample -> log_prob
         ops.mlp_forward(b["sa"], a_tree.flat, sh.obs[t], precision=precision, params_bf16=a_tree.flat_bf16, out=sh.logits, ws_key="learner")
         ops.categorical(sh.logits, None, seeds[0] + u, t, b["roll_ctr"], out=(sh.action[t], sh.log_prob[t]))
@@ -202,7 +216,7 @@ def get_learner_fn(
         D = sa.sizes[0]
         a_tree = state.params.actor_params
         fused = (precision == ops.STX_PREC_BF16 and bool(arch.get("fused_rollout", True)) and E % 128 == 0
-                 and getattr(env, "fused_rollout_supported", False))
+                 and getattr(env, "fused_rollout_supported", False) and b["rs"] is None)
         for u in range(U):
             sh: _Shard = b["shards"][u]
             if fused:  # whole T-step scan in one persistent launch (envs whose dynamics ignore the action)
@@ -210,11 +224,25 @@ def get_learner_fn(
             else:
                 for t in range(T):
                     _env_step(state, u, t, state.key)
+            if b["rs"] is not None:  # bootstrap observations, same pre-update statistics (ff_ppo.py:113-115), one launch
+                ops.obs_normalize(sh.next_obs_raw, b["rs"].mean, b["rs"].std, out=sh.next_obs)
             # value = critic(obs_t), bootstrap_value = critic(next_obs_t) (ff_ppo.py:99,113-116), batched
             ops.mlp_forward(sc, c_tree.flat, sh.obs[:T].view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
                             out=sh.value.view(B, 1), ws_key="learner")
             ops.mlp_forward(sc, c_tree.flat, sh.next_obs.view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
                             out=sh.bootstrap_value.view(B, 1), ws_key="learner")
+
+    def _stats_phase(state: OnPolicyLearnerState) -> None:
+        """UPDATE RUNNING STATISTICS (ff_ppo.py:145-162) with the raw trajectory observations of every shard ("batch")
+        and rank ("device"), std limits 5e-4 / 5e4.  Runs after the rollout: everything in this update that is
+        normalised (rollout inputs, the minibatch observations of the epochs) used the statistics from before it."""
+        b = built
+        if b["rs"] is None:
+            return
+        from stoix_b200.utils import running_statistics as rstat
+
+        rstat.update_statistics_(b["rs"], [sh.obs_raw[:T] for sh in b["shards"]], std_min_value=5e-4, std_max_value=5e4,
+                                 pmap_axes=["device", "batch"], validate_shapes=False, sums=b["rs_sums"])
 
     def _gae_phase(state: OnPolicyLearnerState) -> None:
         """CALCULATE ADVANTAGE (ff_ppo.py:164-179)."""
@@ -296,7 +324,7 @@ def get_learner_fn(
         (learner_state.timestep of ff_ppo.py:131-134); the finished trajectory stays readable until then."""
         for u in range(U):
             sh = built["shards"][u]
-            sh.obs[0].copy_(sh.obs[T])
+            sh.env_obs[0].copy_(sh.env_obs[T])
 
     def _advance_phase(state: OnPolicyLearnerState) -> None:
         """Advance the device-resident RNG stream positions (graph replays then draw fresh numbers)."""
@@ -316,6 +344,7 @@ def get_learner_fn(
         with torch.cuda.stream(side):
             _shuffle_phase(state)
         _rollout_phase(state)
+        _stats_phase(state)
         _gae_phase(state)
         main.wait_stream(side)  # join
         _update_phase(state, shuffled=True)
@@ -361,20 +390,20 @@ def get_learner_fn(
                 ep_out["is_terminal_step"][k, u].copy_(sh.is_terminal_step)
             train_out[k].copy_(b["metrics"])
         # the observation the next learn() call starts from
-        new_ts = [learner_state.timestep[u]._replace(observation=b["shards"][u].obs[T]) for u in range(U)]
+        new_ts = [learner_state.timestep[u]._replace(observation=b["shards"][u].env_obs[T]) for u in range(U)]
         learner_state = learner_state._replace(timestep=new_ts)
         train_metrics = {name: train_out[..., j] for j, name in enumerate(_METRIC_NAMES)}
         return AnakinExperimentOutput(learner_state=learner_state, episode_metrics=ep_out, train_metrics=train_metrics)
 
     learner_fn.built = built  # exposed for tests / bench (trajectory buffers, graph handle)
     learner_fn.update_step = _update_step
-    learner_fn.phases = {"rollout": _rollout_phase, "gae": _gae_phase, "update": _update_phase}
+    learner_fn.phases = {"rollout": _rollout_phase, "stats": _stats_phase, "gae": _gae_phase, "update": _update_phase}
 
     def _ensure_built(st: OnPolicyLearnerState) -> None:
         if not built:
             _build(st)
             for u in range(U):  # last_timestep.observation seeds the carry slot (row T)
-                built["shards"][u].obs[T].copy_(st.timestep[u].observation)
+                built["shards"][u].env_obs[T].copy_(st.timestep[u].observation)
 
     learner_fn.ensure_built = _ensure_built
     return learner_fn
@@ -469,9 +498,38 @@ def learner_setup(
     init_learner_state = OnPolicyLearnerState(
         params=params, opt_states=opt_states, key=(rollout_seed, shuffle_seed), env_state=env_states, timestep=timesteps,
     )
+    # If normalizing observations, initialize running statistics from warm-up rollouts (ff_ppo.py:539-549); this adds a
+    # `running_statistics` field to the learner state.
     if config.system.normalize_observations:
-        raise NotImplementedError("normalize_observations=True is a 'next' row (SURVEY.md 8f #2) and not built yet")
+        from stoix_b200.utils import running_statistics as rstat
+
+        warmup_observations = _collect_obs_norm_rollouts(env, key, config)
+        running_statistics = rstat.initialize_statistics_from_data(init_x[0], warmup_observations)
+        init_learner_state = rstat.create_with_running_statistics(init_learner_state, running_statistics)
     return learn, actor_network, init_learner_state
+
+
+def _collect_obs_norm_rollouts(env: Environment, key: int, config: DictConfig) -> torch.Tensor:
+    """Collect observations for observation normalisation by taking uniformly random actions for
+    system.obs_norm_warmup_steps steps (ff_ppo.py:375-421); not counted in the timestep budget.
+    Returns (warmup_steps + 1, num_envs, *obs_shape) raw observations of this rank's env shard."""
+    steps, E = int(config.system.obs_norm_warmup_steps), int(config.arch.num_envs)
+    if _world()[0] == 0:
+        print(f"Initializing observation normalization with {steps * int(config.arch.total_num_envs)} observations... "
+              "Be aware, we do not count this in the timestep budget.")
+    keys = srandom.split(key, E + 1)
+    if hasattr(env, "seed"):
+        env.seed = (int(config.arch.seed) + 104729 * (_world()[0] + 1)) & ((1 << 63) - 1)
+    env_state, ts = env.reset(keys[:E])
+    dev = ts.observation.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(keys[E]) & ((1 << 62) - 1))
+    obs = [ts.observation.float().clone()]
+    for _ in range(steps):
+        action = torch.randint(0, int(config.system.action_dim), (E,), device=dev, generator=gen, dtype=torch.int32)
+        env_state, ts = env.step(env_state, action)
+        obs.append(ts.observation.float().clone())
+    return torch.stack(obs, 0)
 
 
 def get_final_step_metrics(metrics: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], bool]:
@@ -539,7 +597,8 @@ def run_experiment(_config: DictConfig) -> float:
 
         start_time = time.time()
         trained_params = learner_output.learner_state.params.actor_params
-        evaluator_output = evaluator(trained_params, srandom.split(key_e, eval_step + 2)[-1])
+        evaluator_output = evaluator(trained_params, srandom.split(key_e, eval_step + 2)[-1],
+                                     running_statistics=getattr(learner_state, "running_statistics", None))
         torch.cuda.synchronize()
         elapsed_time = time.time() - start_time
         episode_return = float(evaluator_output["episode_return"].mean().item())
@@ -562,7 +621,8 @@ def run_experiment(_config: DictConfig) -> float:
         best_tree = build_param_tree(learner_state.params.actor_params.spec, best_params, "action_head")
         if learner_state.params.actor_params.flat_bf16 is not None:
             best_tree.flat_bf16 = ops.cast_bf16(best_params)
-        evaluator_output = absolute_metric_evaluator(best_tree, srandom.split(key_e, 1)[0])
+        evaluator_output = absolute_metric_evaluator(best_tree, srandom.split(key_e, 1)[0],
+                                                     running_statistics=getattr(learner_state, "running_statistics", None))
         torch.cuda.synchronize()
         elapsed_time = time.time() - start_time
         steps_per_eval = int(evaluator_output["episode_length"].sum().item())
