@@ -140,6 +140,11 @@ int stx_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t
 int stx_tc_debug_forward(const StxMlp* mlp, const void* x, int64_t ldx, int64_t M, float* out, float* h1,
                          float* h2, void* stream);
 
+/* Grid cap (CTAs) of the persistent bf16 forward kernel for the stx_mlp_forward launches that follow; 0 = one CTA per SM.
+ * Lets a forward pass run beside another persistent kernel (the learner evaluates the critic on the SMs the rollout
+ * kernel leaves idle) instead of queueing CTAs behind it.  Host-side state, read at launch time. */
+void stx_tc_set_forward_ctas(int n);
+
 /* Profiling hook: device buffer of >= 32 int64 that K3a's CTA 0 fills with clock64() stamps of its second
  * tile (MMA-warp slots 0..9, first epilogue warp slots 16..27); NULL disables.  Synchronous (not for capture). */
 int stx_tc_debug_set_clock_buffer(long long* buf);

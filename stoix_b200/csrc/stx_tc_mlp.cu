@@ -324,6 +324,8 @@ int make_map_tiled(CUtensorMap* m, const void* base, uint64_t tiles, uint32_t co
   return STX_OK;
 }
 
+static int g_forward_ctas = 0;  // stx_tc_set_forward_ctas: grid cap of the persistent forward kernel (0 = all SMs)
+
 static bool tc_shape_ok(const StxMlp* m) {
   return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
          m->sizes[3] >= 1 && m->sizes[3] <= 16;
@@ -354,7 +356,8 @@ int tc_forward_impl(const StxMlp* m, const void* x, int64_t ldx, int64_t M, floa
     STX_CUDA_OK(cudaFuncSetAttribute(tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int cap = (g_forward_ctas > 0 && g_forward_ctas < kNumSMs) ? g_forward_ctas : kNumSMs;
+  const int grid = p.num_tiles < cap ? p.num_tiles : cap;
   tc_mlp_fwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmX, tmW0, tmW1, p);
   STX_LAUNCH_OK();
   return STX_OK;
@@ -371,6 +374,8 @@ int tc_mlp_forward(const StxMlp* mlp, const void* x, int64_t ldx, const int32_t*
 }
 
 }  // namespace stx
+
+extern "C" void stx_tc_set_forward_ctas(int n) { stx::tc::g_forward_ctas = n; }
 
 // Bring-up / test hook: forward that also returns the bf16-rounded hidden activations.
 extern "C" int stx_tc_debug_forward(const StxMlp* mlp, const void* x, int64_t ldx, int64_t M, float* out, float* h1, float* h2,

@@ -84,14 +84,18 @@ class SyntheticBoxEnv(Environment):
     # -- whole-rollout face (bf16 tensor-core path) ---------------------------------------------------
     fused_rollout_supported = True
 
-    def fused_rollout(self, state, actor_spec, actor_params, actor_params_bf16, shard, T: int, cat_seed: int, cat_counter) -> None:
-        """All T steps of policy + env in one persistent kernel (stx_tc_rollout_synth).  Valid because this
-        env's dynamics ignore the action, so the kernel generates step t+1's observation while the tensor cores
-        evaluate step t; the trajectory is bit-identical to T calls of step_into."""
-        ops.tc_rollout_synth(actor_spec, actor_params, actor_params_bf16, shard.obs, shard.next_obs, shard.action, shard.log_prob,
-                             shard.reward, shard.done, shard.truncated, shard.episode_return, shard.episode_length,
-                             shard.is_terminal_step, state["run_return"], state["run_length"], state["seed"], 0, state["counter"],
-                             self.p_term, self.p_trunc, cat_seed, 0, cat_counter)
+    def fused_rollout(self, state, actor_spec, actor_params, actor_params_bf16, shard, T: int, cat_seed: int, cat_counter,
+                      t0: int = 0, steps: int = None) -> None:
+        """Steps [t0, t0 + steps) of policy + env in one persistent kernel (stx_tc_rollout_synth); default: all T.  Valid
+        because this env's dynamics ignore the action, so the kernel generates step t+1's observation while the tensor
+        cores evaluate step t; the trajectory is bit-identical to T calls of step_into (and to any chunking: the RNG
+        counters are (env, absolute step))."""
+        n = T - t0 if steps is None else int(steps)
+        a, b = t0, t0 + n
+        ops.tc_rollout_synth(actor_spec, actor_params, actor_params_bf16, shard.obs[a:b + 1], shard.next_obs[a:b], shard.action[a:b],
+                             shard.log_prob[a:b], shard.reward[a:b], shard.done[a:b], shard.truncated[a:b], shard.episode_return[a:b],
+                             shard.episode_length[a:b], shard.is_terminal_step[a:b], state["run_return"], state["run_length"],
+                             state["seed"], a, state["counter"], self.p_term, self.p_trunc, cat_seed, a, cat_counter)
 
     def advance(self, state, steps: int) -> None:
         """Move the device-resident step counter (end of a rollout; graph-capturable)."""

@@ -184,6 +184,15 @@ def mlp_forward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, row_idx: O
     return out
 
 
+NUM_SMS = 148
+
+
+def set_forward_cta_budget(n: int) -> None:
+    """Cap the grid of the persistent bf16 forward kernel for the launches that follow (0 = all SMs).  Host-side switch,
+    read at launch (and therefore baked into a captured graph): used to run the critic next to the rollout kernel."""
+    _lib.load().stx_tc_set_forward_ctas(int(n))
+
+
 def tc_debug_forward(spec: MlpSpec, params: torch.Tensor, params_bf16: torch.Tensor, x: torch.Tensor):
     """bf16 tensor-core forward returning (out, h1, h2) -- test hook."""
     dev = _need_cuda(params, params_bf16, x)

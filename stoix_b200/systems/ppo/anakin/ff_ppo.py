@@ -177,6 +177,7 @@ def get_learner_fn(
             roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # categorical call index
             perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),   # shuffle stream index
             side_stream=torch.cuda.Stream(device=dev),                # the shuffles run here, underneath the rollout
+            critic_stream=torch.cuda.Stream(device=dev),              # chunked critic evaluation underneath the fused rollout
             rs=rs, rs_sums=torch.zeros(2 * D + 1, dtype=torch.float64, device=dev) if rs is not None else None,
             graph=None, eager_done=False,
         )
@@ -217,20 +218,48 @@ def get_learner_fn(
         a_tree = state.params.actor_params
         fused = (precision == ops.STX_PREC_BF16 and bool(arch.get("fused_rollout", True)) and E % 128 == 0
                  and getattr(env, "fused_rollout_supported", False) and b["rs"] is None)
+        # The two critic evaluations of _env_step (value = critic(obs_t), bootstrap_value = critic(next_obs_t), ff_ppo.py:99,
+        # 113-116) depend only on the observations, so they are batched over (steps x envs) rows.  With the fused rollout
+        # (E/128 of the 148 SMs busy) the scan is cut into chunks and the critic of chunk c runs on a second stream on the
+        # idle SMs while the rollout kernel produces chunk c+1; only the last chunk's critic is left after the scan.
+        chunks = max(int(arch.get("rollout_chunks", 8)), 1) if fused else 1
+        while T % chunks != 0:  # largest divisor of T not above the request
+            chunks -= 1
+        Tc = T // chunks
+        main = torch.cuda.current_stream()
+        side = b["critic_stream"] if chunks > 1 else None
+
+        def critic_rows(sh: _Shard, t_lo: int, t_hi: int) -> None:
+            n = (t_hi - t_lo) * E
+            ops.mlp_forward(sc, c_tree.flat, sh.obs[t_lo:t_hi].view(n, D), precision=precision, params_bf16=c_tree.flat_bf16,
+                            out=sh.value[t_lo:t_hi].view(n, 1), ws_key="learner-critic")
+            ops.mlp_forward(sc, c_tree.flat, sh.next_obs[t_lo:t_hi].view(n, D), precision=precision, params_bf16=c_tree.flat_bf16,
+                            out=sh.bootstrap_value[t_lo:t_hi].view(n, 1), ws_key="learner-critic")
+
         for u in range(U):
             sh: _Shard = b["shards"][u]
-            if fused:  # whole T-step scan in one persistent launch (envs whose dynamics ignore the action)
-                env.fused_rollout(state.env_state[u], sa, a_tree.flat, a_tree.flat_bf16, sh, T, state.key[0] + u, b["roll_ctr"])
+            if fused:  # persistent launches (envs whose dynamics ignore the action), `chunks` of Tc steps each
+                for c in range(chunks):
+                    env.fused_rollout(state.env_state[u], sa, a_tree.flat, a_tree.flat_bf16, sh, T, state.key[0] + u, b["roll_ctr"],
+                                      t0=c * Tc, steps=Tc)
+                    if side is not None:
+                        side.wait_stream(main)
+                        with torch.cuda.stream(side):
+                            # leave the rollout's SMs alone: a persistent forward CTA that has to wait for one of them
+                            # would hold its share of the tiles back until the rollout chunk ends
+                            ops.set_forward_cta_budget(ops.NUM_SMS - E // 128 if c + 1 < chunks else 0)
+                            critic_rows(sh, c * Tc, (c + 1) * Tc)
+                            ops.set_forward_cta_budget(0)
+                if side is not None:
+                    main.wait_stream(side)
+                else:
+                    critic_rows(sh, 0, T)
             else:
                 for t in range(T):
                     _env_step(state, u, t, state.key)
-            if b["rs"] is not None:  # bootstrap observations, same pre-update statistics (ff_ppo.py:113-115), one launch
-                ops.obs_normalize(sh.next_obs_raw, b["rs"].mean, b["rs"].std, out=sh.next_obs)
-            # value = critic(obs_t), bootstrap_value = critic(next_obs_t) (ff_ppo.py:99,113-116), batched
-            ops.mlp_forward(sc, c_tree.flat, sh.obs[:T].view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
-                            out=sh.value.view(B, 1), ws_key="learner")
-            ops.mlp_forward(sc, c_tree.flat, sh.next_obs.view(B, D), precision=precision, params_bf16=c_tree.flat_bf16,
-                            out=sh.bootstrap_value.view(B, 1), ws_key="learner")
+                if b["rs"] is not None:  # bootstrap observations, same pre-update statistics (ff_ppo.py:113-115), one launch
+                    ops.obs_normalize(sh.next_obs_raw, b["rs"].mean, b["rs"].std, out=sh.next_obs)
+                critic_rows(sh, 0, T)
 
     def _stats_phase(state: OnPolicyLearnerState) -> None:
         """UPDATE RUNNING STATISTICS (ff_ppo.py:145-162) with the raw trajectory observations of every shard ("batch")
