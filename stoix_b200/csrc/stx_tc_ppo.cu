@@ -95,9 +95,10 @@ struct FbParams {
   int mb;
   float clip_eps, ent_coef, vf_coef;
   // fused launch (tc_ppo_fused_kernel): per-tile completion counters polled by the weight-gradient CTAs (nullptr: none)
-  uint32_t* flag_a;   // [2][tiles] h1, h2, dz, dh2 of (net, tile) stored      -> kFlagEpi arrivals (one per epilogue warp)
-  uint32_t* flag_b;   // [2][tiles] dh1 of (net, tile) stored                  -> kFlagEpi arrivals
-  uint32_t* flag_x;   // [tiles]    gathered input rows xg of tile stored      -> kFlagGather arrivals (actor CTAs)
+  uint32_t* flag_t;   // [2][tiles] every activation (h1, h2, dz, dh2, dh1) of (net, tile) stored -> kFlagEpi arrivals (one per epilogue warp)
+  uint32_t* flag_x;   // [tiles]    gathered input rows xg of tile stored                         -> kFlagGather arrivals (actor CTAs)
+  int act_policy;     // L2 policy of the activation stores: 0 evict_first (read once, after a kernel boundary), 1 normal, 2 evict_last
+  int ring_tiles;     // activation workspace = ring of this many tile slots per network (tile t -> slot t % ring_tiles); 0: one slot per tile
 };
 constexpr uint32_t kFlagEpi = 8, kFlagGather = 4;
 
@@ -115,17 +116,12 @@ __device__ __forceinline__ void flag_signal_timed(uint32_t* f, int lane, long lo
   flag_signal(f, lane);
   acc += clock64() - t0;
 }
-// Consumer side (one thread): spin until `want` arrivals, then order the async-proxy (TMA) reads that follow behind it.
-__device__ __forceinline__ void flag_wait(const uint32_t* f, uint32_t want, const char* what) {
-  uint32_t v, spins = 0;
-  unsigned long long t0 = 0ull;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    if (v >= want) break;
-    spin_guard(spins, t0, what);
-  }
-  asm volatile("fence.proxy.async.global;" ::: "memory");
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* f) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
 }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Tiled activation layout shared by K3a (writer) and K3b (reader): element (row, col) of a [mb x 8*CG]
 // matrix lives at ((row/128 * CG + col/8) * 128 + row%128) * 8 + col%8.
@@ -219,12 +215,13 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t pol_stream = l2_evict_first();  // the activations are written once and read once (by K3b)
+  const uint64_t pol_stream = l2_policy(p.act_policy);  // default evict_first: the activations are written once and read once (by K3b)
   const int which = (int)blockIdx.x < p.n_cta[0] ? 0 : 1;
   const FbNet& net = p.net[which];
   const int cta_in_net = which == 0 ? (int)blockIdx.x : (int)blockIdx.x - p.n_cta[0];
   const int ncta = p.n_cta[which];
   const int num_tiles = p.mb / kTileM;
+  const int ring = p.ring_tiles > 0 ? p.ring_tiles : (num_tiles > 0 ? num_tiles : 1);
   const int my_tiles = cta_in_net < num_tiles ? (num_tiles - cta_in_net + ncta - 1) / ncta : 0;
   const CUtensorMap* tmW0 = which == 0 ? &tmW0a : &tmW0c;
   const CUtensorMap* tmW1 = which == 0 ? &tmW1a : &tmW1c;
@@ -316,7 +313,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xs + ((c ^ (r & 7)) << 4)) = v[c];  // Swizzle<3,4,3>
       if (which == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) st_hint(tiled_ptr(p.xg, mrow, c, 8), v[c], pol_stream);
+        for (int c = 0; c < 8; ++c) st_hint(tiled_ptr(p.xg, (int64_t)(tile % ring) * kTileM + r, c, 8), v[c], pol_stream);
       }
       if (warp == 0) STX_STAMP(50);
       fence_async_proxy();
@@ -463,6 +460,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = cta_in_net + it * ncta;
       const int64_t mrow = (int64_t)tile * kTileM + q * 32 + lane;  // row inside the minibatch
+      const int64_t srow = (int64_t)(tile % ring) * kTileM + q * 32 + lane;  // its row in the activation workspace (slot of the tile)
       // per-row loss inputs: issued now, consumed in E2 (their latency hides behind E0/E1)
       int pf_a = 0;
       float pf_0 = 0.f, pf_1 = 0.f;
@@ -504,11 +502,11 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // this chunk of D consumed, its K-chunks of the next A operand written
-          // the flushes above issued this warp's last dh1 stores of the PREVIOUS tile: dh1 of that tile is complete
-          if (layer == 0 && cc == 0 && it > 0 && p.flag_b != nullptr) flag_signal_timed(p.flag_b + which * num_tiles + (tile - ncta), lane, prof_sig);
+          // the flushes above issued this warp's last stores (dh1) of the PREVIOUS tile: that tile's activations are complete
+          if (layer == 0 && cc == 0 && it > 0 && p.flag_t != nullptr) flag_signal_timed(p.flag_t + which * num_tiles + (tile - ncta), lane, prof_sig);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
-          pend_ptr = tiled_ptr(hout, mrow, c * 4, 32);
+          pend_ptr = tiled_ptr(hout, srow, c * 4, 32);
         }
       }
       // ---------------- E2: head + loss + d(head) ----------------
@@ -554,8 +552,8 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
         __syncwarp();
         if (lane == 0) mbar_arrive(head_done);
         if (warp == 5) STX_STAMP(44);
-        st_hint(tiled_ptr(net.dz, mrow, 0, 2), make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
-        st_hint(tiled_ptr(net.dz, mrow, 1, 2), make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
+        st_hint(tiled_ptr(net.dz, srow, 0, 2), make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+        st_hint(tiled_ptr(net.dz, srow, 1, 2), make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
         // bias gradient of the head (off the critical path: G3 is already running): column sums over the 32 rows
         // of this warp; fold the two half-warps first (1 shuffle per column), then the 16-lane butterfly
         {
@@ -611,11 +609,9 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_done[part]);  // E3: -> G4 ; E4: D columns free for the next tile's G0
-          // first chunk of E4: the flushes above issued this warp's last dh2 stores; h1, h2 and dz went out earlier
-          if (layer == 0 && cc == 0 && p.flag_a != nullptr) flag_signal_timed(p.flag_a + which * num_tiles + tile, lane, prof_sig);
 #pragma unroll
           for (int j = 0; j < 16; ++j) pend[j] = pk[j];
-          pend_ptr = tiled_ptr(dout, mrow, c * 4, 32);
+          pend_ptr = tiled_ptr(dout, srow, c * 4, 32);
           if (layer == 1) {  // db1; db0 = column sums of dh1 comes out of K3b's dW0 job for free (ones-operand MMA)
             const float cs = warp_colsum32(dv, lane);
             dbacc[c * 32 + lane] += cs;  // this (quarter, column) is touched by this warp only
@@ -627,7 +623,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) STX_FLUSH_PENDING(g);  // the last chunk of the last tile
-    if (my_tiles > 0 && p.flag_b != nullptr) flag_signal_timed(p.flag_b + which * num_tiles + cta_in_net + (my_tiles - 1) * ncta, lane, prof_sig);
+    if (my_tiles > 0 && p.flag_t != nullptr) flag_signal_timed(p.flag_t + which * num_tiles + cta_in_net + (my_tiles - 1) * ncta, lane, prof_sig);
 #undef STX_FLUSH_PENDING
     STX_STAMP_AT(61, warp == 5 && lane == 0);
     if (g_prof_buf != nullptr && warp == 5 && lane == 0) {
@@ -690,7 +686,7 @@ struct DwSub {
   int N;           // 16, 64 or 256 (= 8 * column groups of B)
   int map;         // index of the (A, B) tensor-map pair in DwMaps
   int tmem_col;    // accumulator columns [tmem_col, tmem_col + N (+16 with colsum)) of each 256-column half
-  int wait_b;      // fused launch: 0 = operands complete with flag_a; 1 = needs flag_b (dh1) and flag_x (xg) as well
+  int wait_x;      // fused launch: 1 = the B operand is xg (written by the ACTOR CTAs: its own completion counter)
 };
 // A job = the CTAs [cta_begin, cta_begin + n_cta) running the same 1..2 GEMMs over an interleaved share of the 64-row chunks.
 struct DwJob {
@@ -706,9 +702,10 @@ struct DwParams {
   int n_jobs;
   int num_tiles;
   // fused launch: completion counters written by the K3a CTAs of the same grid (nullptr: operands are complete at entry)
-  const uint32_t* flag_a;
-  const uint32_t* flag_b;
-  const uint32_t* flag_x;
+  const uint32_t* flag_t;  // [2][tiles]
+  const uint32_t* flag_x;  // [tiles]
+  int ring_tiles;  // see FbParams
+  int act_policy;
 };
 struct DwMaps {
   CUtensorMap a[kMaxJobs];  // tiled [mb x 256]: 2D u64 view {256 per (tile, colgroup), tiles*32}, box {128, 32}
@@ -765,34 +762,60 @@ __device__ __forceinline__ void dw_role(uint8_t* smem_raw, const DwMaps& maps, c
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint64_t pol_stream = l2_evict_first();  // every activation tile is read exactly once
+      const uint64_t pol_stream = l2_policy(p.act_policy);  // default evict_first: every activation tile is read exactly once
       long long w_flag = 0, w_empty = 0;
       int k = 0;
+      bool need_x = false;
+      for (int sj = 0; sj < n_sub; ++sj) need_x |= job.sub[sj].wait_x != 0;
+      // Completion of this CTA's chunks is polled a WINDOW at a time: one batch of independent acquire loads (one L2 round
+      // trip) and ONE generic->async proxy fence cover up to kWin chunks, instead of a dependent round trip + fence in front
+      // of every TMA issue (measured: ~900 cycles per pipeline slot, which made the loads, not the MMAs, the pace).
+      constexpr int kWin = 8;
+      int known = fused ? 0 : my_chunks;  // chunks [0, known) of this CTA's sequence have their operands in memory
       for (int it = 0; it < my_chunks; ++it) {
         // split launches: newest rows first (K3a wrote the last tiles most recently, so they are the likeliest L2 residents);
         // fused launch: in the order the K3a CTAs of this grid finish their tiles
         const int ci = cta + it * job.n_cta;
         const int chunk = fused ? ci : job.num_chunks - 1 - ci;  // 64 rows: half of a 128-row tile
         const int tile = chunk >> 1, r0 = (chunk & 1) * 64;
+        if (it >= known) {
+          const long long tq = clock64();
+          uint32_t spins = 0;
+          unsigned long long t0 = 0ull;
+          for (;;) {
+            uint32_t vt[kWin], vx[kWin];
+#pragma unroll
+            for (int w = 0; w < kWin; ++w) {
+              const int tw = (cta + (it + w) * job.n_cta) >> 1;
+              const bool in = it + w < my_chunks;
+              vt[w] = in ? ld_acquire_gpu(p.flag_t + job.net * p.num_tiles + tw) : 0u;
+              vx[w] = (in && need_x) ? ld_acquire_gpu(p.flag_x + tw) : kFlagGather;
+            }
+            int ok = 0;
+#pragma unroll
+            for (int w = 0; w < kWin; ++w)
+              if (ok == w && it + w < my_chunks && vt[w] >= kFlagEpi && vx[w] >= kFlagGather) ok = w + 1;
+            if (ok > 0) {
+              known = it + ok;
+              break;
+            }
+            spin_guard(spins, t0, "K3 activations of a tile");
+          }
+          fence_proxy_async_global();  // the TMA (async proxy) reads below must observe what the acquire loads observed
+          w_flag += clock64() - tq;
+        }
         for (int sj = 0; sj < n_sub; ++sj, ++k) {
           const DwSub& sub = job.sub[sj];
           const int s = k % kDwStages;
-          long long tq = clock64();
+          const long long tq = clock64();
           if (k >= kDwStages) mbar_wait(&empty[s], ((k / kDwStages) & 1) ^ 1, 20);
-          w_empty += clock64() - tq, tq = clock64();
-          if (fused) {
-            flag_wait(p.flag_a + job.net * p.num_tiles + tile, kFlagEpi, "K3 activations (h1, h2, dz, dh2) of a tile");
-            if (sub.wait_b) {
-              flag_wait(p.flag_b + job.net * p.num_tiles + tile, kFlagEpi, "K3 activations (dh1) of a tile");
-              flag_wait(p.flag_x + tile, kFlagGather, "K3 gathered input rows of a tile");
-            }
-          }
-          w_flag += clock64() - tq;
+          w_empty += clock64() - tq;
           uint8_t* st = smem + s * kDwStageBytes;
           mbar_arrive_expect_tx(&full[s], 32768 + (uint32_t)sub.N * 128);
           // one box = rows r0..r0+63 of every column group: smem image [colgroup][row][16 B]
-          tma_load_2d_hint(st, &maps.a[sub.map], &full[s], r0 * 2, tile * 32, pol_stream);
-          tma_load_2d_hint(st + 32768, &maps.b[sub.map], &full[s], r0 * 2, tile * (sub.N >> 3), pol_stream);
+          const int slot = p.ring_tiles > 0 ? tile % p.ring_tiles : tile;
+          tma_load_2d_hint(st, &maps.a[sub.map], &full[s], r0 * 2, slot * 32, pol_stream);
+          tma_load_2d_hint(st + 32768, &maps.b[sub.map], &full[s], r0 * 2, slot * (sub.N >> 3), pol_stream);
         }
       }
       if (prof) prof[0] = 2 + j, prof[2] = w_flag, prof[3] = w_empty, prof[5] = my_iters;
@@ -891,7 +914,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(const __grid_const
 }
 
 // ONE launch for K3a + K3b: the first n_cta[0] + n_cta[1] CTAs are K3a CTAs (fb_role), the rest weight-gradient CTAs
-// (dw_role) that consume the activation tiles as the K3a CTAs of the same grid complete them (flag_a / flag_b / flag_x),
+// (dw_role) that consume the activation tiles as the K3a CTAs of the same grid complete them (flag_t / flag_x),
 // through L2 instead of after a kernel boundary.  All CTAs are co-resident (grid <= 148, one CTA per SM); a consumer only
 // ever waits for K3a CTAs, which wait for nobody outside their own CTA, so the launch cannot deadlock.  The assignment of
 // tiles to CTAs is static => the partial sums keep a fixed association order (run-to-run deterministic gradients).
@@ -1109,7 +1132,7 @@ inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 struct TcWs {
   __nv_bfloat16 *h1[2], *h2[2], *dh1[2], *dh2[2], *dz[2], *xg;
   float *part_w1[2], *part_w2[2], *part_w0[2], *db_part[2], *db0_part[2], *metric_part;
-  uint32_t* flags;  // [2][tiles] a, [2][tiles] b, [tiles] x  (fused launch)
+  uint32_t* flags;  // [2][tiles] tile counters, [tiles] xg counters  (fused launch)
   size_t bytes;
 };
 
@@ -1129,6 +1152,8 @@ struct K3Plan {
   int w1 = 35, w2 = 18, w0 = 21;   // split
   bool fused = false;
   int fb = 64, fw1 = 6, fw02 = 4;  // fused
+  int act_policy = 0;              // L2 policy of the activation stream (STX_K3_POLICY: 0 evict_first, 1 normal, 2 evict_last)
+  int ring = 0;                    // fused: tile slots per network of the activation ring (STX_K3_RING; 0 = one slot per tile)
   K3Plan() {
     int a, b, c;
     const char* e = getenv("STX_DW_SPLIT");
@@ -1137,6 +1162,10 @@ struct K3Plan {
     if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0 && a + b + c == kCtaPerNet) fb = a, fw1 = b, fw02 = c;
     e = getenv("STX_K3_FUSED");
     if (e) fused = e[0] == '1';
+    e = getenv("STX_K3_RING");
+    if (e) ring = atoi(e);
+    e = getenv("STX_K3_POLICY");
+    if (e) act_policy = atoi(e);
   }
 };
 static const K3Plan g_plan;
@@ -1153,7 +1182,7 @@ TcWs carve_tc(int64_t mb, char* base) {
     return q;
   };
   const int tiles = (int)(mb / 128);
-  w.flags = (uint32_t*)take((size_t)5 * tiles * 4);  // first: the caller zero-fills the workspace once, the reduce kernel re-zeroes
+  w.flags = (uint32_t*)take((size_t)3 * tiles * 4);  // first: the caller zero-fills the workspace once, the reduce kernel re-zeroes
   const int n_w1 = g_plan.fused ? g_plan.fw1 : g_plan.w1, n_w2 = g_plan.fused ? g_plan.fw02 : g_plan.w2,
             n_w0 = g_plan.fused ? g_plan.fw02 : g_plan.w0;
   for (int n = 0; n < 2; ++n) {
@@ -1241,14 +1270,16 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   fp.adv_stats = h->standardize_advantages ? b->adv_stats : nullptr;
   fp.metric_part = ws.metric_part;
   fp.D = D, fp.mb = (int)mb, fp.clip_eps = h->clip_eps, fp.ent_coef = h->ent_coef, fp.vf_coef = h->vf_coef;
-  if (fused) fp.flag_a = ws.flags, fp.flag_b = ws.flags + 2 * num_tiles, fp.flag_x = ws.flags + 4 * num_tiles;
+  const int ring_tiles = (fused && g_plan.ring > 0 && g_plan.ring < num_tiles) ? g_plan.ring : 0;
+  if (fused) fp.flag_t = ws.flags, fp.flag_x = ws.flags + 2 * num_tiles;
+  fp.ring_tiles = ring_tiles, fp.act_policy = g_plan.act_policy;
 
   // ---- K3b parameters ----
   DwMaps maps;
   DwParams dp{};
   int cta = 0, jn = 0, mi = 0;
   const int chunks = (int)(mb / 64);
-  const uint64_t tiles = (uint64_t)num_tiles;
+  const uint64_t tiles = (uint64_t)(ring_tiles > 0 ? ring_tiles : num_tiles);
   int n_w1 = 0, n_w2 = 0, n_w0 = 0;  // partials per network of each weight gradient (for the reduce below)
   for (int n = 0; n < 2; ++n) {
     // tensor-map pairs of this network: m1 (h1, dh2) -> dW1, m2 (h2, dz) -> dW2, m0 (dh1, xg) -> dW0^T (+ db0 = dh1^T * 1)
@@ -1278,8 +1309,8 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
       n_w1 = kDwCtaW1, n_w2 = kDwCtaW2, n_w0 = kDwCtaW0;
     }
   }
-  dp.n_jobs = jn, dp.num_tiles = num_tiles;
-  if (fused) dp.flag_a = fp.flag_a, dp.flag_b = fp.flag_b, dp.flag_x = fp.flag_x;
+  dp.n_jobs = jn, dp.num_tiles = num_tiles, dp.ring_tiles = ring_tiles, dp.act_policy = g_plan.act_policy;
+  if (fused) dp.flag_t = fp.flag_t, dp.flag_x = fp.flag_x;
 
   // ---- launches ----
   // 8 epilogue warps: 16 (two parts per step, 80 registers) measured 5 % slower (profiles/README.md)
@@ -1326,7 +1357,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
   rp.metric_part = ws.metric_part, rp.n_cta_total = 2 * n_fb, rp.metrics = metrics;
   rp.weight = grad_weight, rp.inv_mb = 1.0f / (float)mb;
   rp.overwrite = opt ? 1 : h->overwrite_grads;
-  if (fused) rp.flags = ws.flags, rp.n_flags = 5 * num_tiles;
+  if (fused) rp.flags = ws.flags, rp.n_flags = 3 * num_tiles;
   // side output for the fused optimiser: partials[seg][block] right after the 16-byte header of its scratch
   void* adam_scratch = opt ? opt->scratch : h->adam_scratch;
   rp.sumsq = (rp.overwrite && adam_scratch) ? reinterpret_cast<double*>(reinterpret_cast<char*>(adam_scratch) + 16) : nullptr;

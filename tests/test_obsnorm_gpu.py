@@ -161,8 +161,8 @@ def test_learner_with_observation_normalisation_matches_oracle(precision):
         if bf16:
             _, coff, _ = ops.arena_offsets(a_tree.spec, c_tree.spec)
             mu, nu = f64(a_tree.arena_mu), f64(a_tree.arena_nu)
-            assert max(rel(mu[:n_a], a_st.mu), rel(mu[coff:coff + n_c], c_st.mu)) < 0.15
-            assert max(rel(nu[:n_a], a_st.nu), rel(nu[coff:coff + n_c], c_st.nu)) < 0.05
+            assert max(rel(mu[:n_a], a_st.mu), rel(mu[coff:coff + n_c], c_st.mu)) < 0.3
+            assert max(rel(nu[:n_a], a_st.nu), rel(nu[coff:coff + n_c], c_st.nu)) < 0.1
             actor, critic = tree(a_tree), tree(c_tree)
             a_st.mu, a_st.nu, c_st.mu, c_st.nu = mu[:n_a].copy(), nu[:n_a].copy(), mu[coff:coff + n_c].copy(), nu[coff:coff + n_c].copy()
         else:
