@@ -387,6 +387,11 @@ def get_learner_rollout_fn(config: DictConfig, parameter_server: ParameterServer
 
     def learner_rollout(learner_state: CoreLearnerState, rng_key: int) -> None:
         torch.cuda.set_device(learner_device)
+        # own stream: the legacy default stream would serialise the learner with every actor stream of this device
+        with torch.cuda.stream(torch.cuda.Stream(device=learner_device)):
+            _learner_loop(learner_state, rng_key)
+
+    def _learner_loop(learner_state: CoreLearnerState, rng_key: int) -> None:
         thread_start_time = time.perf_counter()
         learner_policy_version = 0
         timer = TimingTracker(maxlen=10)
@@ -413,8 +418,9 @@ def get_learner_rollout_fn(config: DictConfig, parameter_server: ParameterServer
                     logger.log(dict(loss_info), global_step_count, learner_policy_version, LogEvent.TRAIN)
             if num_evaluation > 0 and async_evaluator is not None:
                 rng_key, eval_key = srandom.split(rng_key, 2)
-                torch.cuda.synchronize(learner_device)
+                torch.cuda.current_stream().synchronize()
                 async_evaluator.submit_evaluation(learner_state, eval_key, eval_step, global_step_count)
+        torch.cuda.current_stream().synchronize()
         learner_rollout.final_state = learner_state
 
     return learner_rollout

@@ -1,11 +1,45 @@
-"""Shape derivation for Anakin systems -- same semantics and derived fields as
-stoix/utils/total_timestep_checker.py:9-131 (`arch.num_envs`, `arch.num_updates`,
+"""Shape derivation -- same semantics and derived fields as stoix/utils/total_timestep_checker.py: Anakin :9-131
+(`arch.num_envs`, `arch.num_updates`, `arch.num_updates_per_eval`), Sebulba :134-287 (`arch.actor.num_envs_per_actor`,
+`arch.learner_parallel_env_consumption`, `arch.local_batch_size`, `arch.global_batch_size`, `arch.num_updates`,
 `arch.num_updates_per_eval`), without the colour printing."""
 from __future__ import annotations
 
 
+def check_total_timesteps_sebulba(config, quiet: bool = False):
+    """total_timestep_checker.py:134-287.  Needs config.num_actor_devices / num_learner_devices / arch.world_size."""
+    arch = config.arch
+    total_actors = int(config.num_actor_devices) * int(arch.actor.actor_per_device)
+    if int(arch.total_num_envs) % total_actors != 0:  # :176-187
+        raise AssertionError(f"The total number of environments ({arch.total_num_envs}) must be divisible by "
+                             f"(num_actor_devices * actor_per_device) = {total_actors}!")
+    per_device = int(arch.total_num_envs) // int(config.num_actor_devices)  # :190-197
+    arch.actor.num_envs_per_actor = int(per_device // int(arch.actor.actor_per_device))
+    arch.learner_parallel_env_consumption = (arch.actor.num_envs_per_actor * int(arch.actor.actor_per_device)
+                                             * int(config.num_actor_devices))  # :200-213
+    arch.local_batch_size = int(int(config.system.rollout_length) * arch.learner_parallel_env_consumption)
+    arch.global_batch_size = arch.local_batch_size * int(arch.world_size)
+    if arch.total_timesteps is None:  # :216-243
+        arch.total_timesteps = int(arch.num_updates) * arch.global_batch_size
+    else:
+        arch.total_timesteps = int(float(arch.total_timesteps))
+        arch.num_updates = int(arch.total_timesteps // arch.global_batch_size)
+    num_evaluation = max(int(arch.num_evaluation), 1)  # :246-263
+    arch.num_updates_per_eval = int(int(arch.num_updates) // num_evaluation)
+    actual = arch.global_batch_size * arch.num_updates_per_eval * num_evaluation
+    if not quiet and actual != arch.total_timesteps:
+        print(f"[stoix_b200] Timestep discrepancy: expected {arch.total_timesteps:,}, actual {actual:,}.")
+    if int(arch.num_updates) <= num_evaluation:  # :281-289
+        raise AssertionError(f"Number of updates ({arch.num_updates}) must be greater than number of evaluations ({num_evaluation}).")
+    if arch.learner_parallel_env_consumption % int(config.num_learner_devices) != 0:
+        raise AssertionError(f"Learner parallel env consumption ({arch.learner_parallel_env_consumption}) must be divisible by "
+                             f"number of learner devices ({config.num_learner_devices}).")
+    return config
+
+
 def check_total_timesteps(config, quiet: bool = False):
-    assert config.arch.architecture_name == "anakin", "only the Anakin architecture is built so far"
+    if config.arch.architecture_name == "sebulba":
+        return check_total_timesteps_sebulba(config, quiet)
+    assert config.arch.architecture_name == "anakin", f"unknown architecture '{config.arch.architecture_name}'"
     n_devices = int(config.num_devices)
     ubs = int(config.arch.update_batch_size)
     divisor = n_devices * ubs
