@@ -43,7 +43,7 @@ def bench(T, E, quads=0, iters=20, flush=True):
 if __name__ == "__main__":
     out = []
     for (T, E) in [(128, 4096), (128, 65536), (128, 1048576)]:
-        for q in (0, 32, 308, 316, 332):
+        for q in (0, 32, 416, 408, 316):
             for fl in (True,):
                 out.append(bench(T, E, q, flush=fl))
                 print(json.dumps(out[-1]), flush=True)

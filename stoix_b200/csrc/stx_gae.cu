@@ -76,8 +76,11 @@ struct GenericIn {  // float discount / lambda / truncation arrays (multistep.py
   }
 };
 
-template <class In, int VEC, int QUADS, int kL = 4>
-__global__ void __launch_bounds__(QUADS* kChunks)
+// MINB: resident blocks per SM the register allocation must allow.  A block runs load -> barrier -> scan -> barrier ->
+// store with nothing overlapped inside it, so HBM only stays busy if ANOTHER block of the same SM is in its load phase
+// meanwhile: the saturating shapes use 2 x 512 threads (<= 64 registers) instead of 1 x 1024.
+template <class In, int VEC, int QUADS, int kL = 4, int MINB = 1>
+__global__ void __launch_bounds__(QUADS* kChunks, MINB)
     gae_scan_kernel(In in, int T, int E, float* __restrict__ adv, float* __restrict__ tgt,
                     int want_stats, double2* __restrict__ partials, unsigned int* counter,
                     float* __restrict__ stats) {
@@ -210,7 +213,15 @@ int launch_gae(const In& in, int T, int E, bool vec4, int standardize, float* ad
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double2* partials = reinterpret_cast<double2*>(reinterpret_cast<char*>(scratch) + 16);
   const int want = standardize != 0;
-  if (vec4 && g_quads_override / 100 == 3) {  // L = 2 timesteps per thread (fewer registers, more resident blocks): code 3xx
+  if (vec4 && (g_quads_override / 100 == 4 || (g_quads_override == 0 && E / 4 >= 65536))) {
+    // several resident blocks per SM (code 4xx; the default for saturating shapes): 416 = 2 x 512 threads, 408 = 4 x 256
+    const int quads = g_quads_override == 0 ? 16 : g_quads_override % 100, total = E / 4;
+    const int grid = (total + quads - 1) / quads;
+    if (quads == 16)
+      gae_scan_kernel<In, 4, 16, 4, 2><<<grid, 16 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+    else
+      gae_scan_kernel<In, 4, 8, 4, 4><<<grid, 8 * kChunks, 0, st>>>(in, T, E, adv, tgt, want, partials, counter, stats);
+  } else if (vec4 && g_quads_override / 100 == 3) {  // L = 2 timesteps per thread (fewer registers, more resident blocks): code 3xx
     const int quads = g_quads_override % 100, total = E / 4;
     const int grid = (total + quads - 1) / quads;
     if (quads == 32)

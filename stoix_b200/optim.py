@@ -44,6 +44,13 @@ class OptState(NamedTuple):
 
 
 class GradientTransformation:
+    """optax.GradientTransformation with `init` / `update` (stoix/systems/ppo/anakin/ff_ppo.py:449-463, 264-273).
+
+    `update(updates, state, params=None) -> (updates, new_state)` is functional like optax: it runs the fused clip + Adam
+    kernel (stx_clip_adam_step, ONE segment) on copies and returns the parameter DELTA, so
+    `apply_updates(params, updates)` reproduces optax's two-step form.  The learner itself does not go through this
+    face: it steps both optimisers in place in one launch over the shared arena and only reads the hyper-parameters."""
+
     def __init__(self, clip: Optional[_Clip], adam_: _Adam):
         self.clip, self.adam = clip, adam_
 
@@ -61,15 +68,44 @@ class GradientTransformation:
         lr = self.adam.learning_rate
         return lr if callable(lr) else None
 
-    def init(self, params) -> None:
-        """Optimiser state lives in the learner's flat mu/nu/count arenas (allocated in learner_setup)."""
-        return None
+    @staticmethod
+    def _flat(x):
+        return x.flat if hasattr(x, "flat") and not hasattr(x, "numel") else x
 
-    def update(self, *args, **kwargs):
-        raise RuntimeError(
-            "stoix_b200 optimisers are applied by the fused stx_clip_adam_step kernel inside the learner; "
-            "the `.update` handle only carries the hyper-parameters"
-        )
+    def init(self, params) -> OptState:
+        """(ScaleByAdamState{count=0, mu=0, nu=0}, ScaleByScheduleState{count=0}) for a flat parameter tensor / ParamTree."""
+        import torch
+
+        p = self._flat(params)
+        z = lambda: torch.zeros(1, dtype=torch.int32, device=p.device)
+        return OptState(z(), torch.zeros_like(p), torch.zeros_like(p), z())
+
+    def update(self, updates, state: OptState, params=None):
+        import torch
+
+        from . import ops
+
+        g = self._flat(updates).contiguous()
+        n = g.numel()
+        pad = (-n) % 4  # the kernel wants 16-byte aligned arenas; a private copy is padded instead of asking the caller
+        buf = lambda src: torch.cat([src.reshape(-1).float(), src.new_zeros(pad, dtype=torch.float32)]) if pad else src.reshape(-1).float().clone()
+        p = torch.zeros(n + pad, dtype=torch.float32, device=g.device)
+        mu, nu, gg = buf(state.mu), buf(state.nu), buf(g)
+        sched = self.schedule
+        plan = ops.AdamPlan([(0, n, self.init_lr, self.max_grad_norm if self.clip is not None else 3.0e38)], g.device,
+                            b1=self.adam.b1, b2=self.adam.b2, eps=self.adam.eps, decay=sched is not None,
+                            steps_per_update=getattr(sched, "steps_per_update", 1), num_updates=getattr(sched, "num_updates", 1))
+        plan.counts[0:1].copy_(state.count.reshape(-1)[:1])
+        plan.counts[1:2].copy_(state.sched_count.reshape(-1)[:1])
+        ops.clip_adam_step(plan, p, gg, mu, nu)
+        new_state = OptState(plan.counts[0:1].clone(), mu[:n].view_as(state.mu), nu[:n].view_as(state.nu), plan.counts[1:2].clone())
+        return p[:n].view_as(g), new_state   # parameters started at zero: what is left is the update -lr * u
+
+
+def apply_updates(params, updates):
+    """optax.apply_updates: params + updates (functional)."""
+    p = GradientTransformation._flat(params)
+    return p + GradientTransformation._flat(updates)
 
 
 def chain(*parts) -> GradientTransformation:

@@ -123,8 +123,18 @@ def get_learner_fn(
     network shapes / optimiser hyper-parameters they carry; the arithmetic runs in the fused kernels.
     """
     actor_apply_fn, critic_apply_fn = apply_fns
-    actor_net, critic_net = actor_apply_fn.__self__, critic_apply_fn.__self__
-    actor_opt, critic_opt = update_fns[0].__self__, update_fns[1].__self__
+    # The arithmetic of apply / update runs inside the fused kernels; what the learner needs from the four callables is the
+    # description they are bound to (layer sizes, optimiser hyper-parameters).  Anything else cannot be honoured silently.
+    def _owner(fn, kind, what):
+        obj = getattr(fn, "__self__", None)
+        if not isinstance(obj, kind):
+            raise TypeError(f"get_learner_fn: {what} must be the bound `{'apply' if kind is not optax.GradientTransformation else 'update'}` of a "
+                            f"stoix_b200 {kind.__name__} (got {fn!r}); arbitrary callables cannot be lowered onto the CUDA kernels")
+        return obj
+
+    actor_net, critic_net = _owner(actor_apply_fn, Actor, "apply_fns[0]"), _owner(critic_apply_fn, Critic, "apply_fns[1]")
+    actor_opt = _owner(update_fns[0], optax.GradientTransformation, "update_fns[0]")
+    critic_opt = _owner(update_fns[1], optax.GradientTransformation, "update_fns[1]")
     rank, world = _world()
 
     sysc, arch = config.system, config.arch

@@ -277,6 +277,8 @@ def get_rollout_fn(env_factory: cpu_envs.EnvFactory, actor_device: torch.device,
                     episode_metrics_storage.clear()
             if num_rollouts > num_updates:
                 break
+        rollout_fn.stats = {**timer.get_all_means(), "local_step_count": local_step_count, "num_rollouts": num_rollouts,
+                            "elapsed_s": time.perf_counter() - thread_start_time, "h2d_bytes": server.h2d_bytes, "d2h_bytes": server.d2h_bytes}
         envs.close()
 
     return rollout_fn
@@ -421,6 +423,8 @@ def get_learner_rollout_fn(config: DictConfig, parameter_server: ParameterServer
                 torch.cuda.current_stream().synchronize()
                 async_evaluator.submit_evaluation(learner_state, eval_key, eval_step, global_step_count)
         torch.cuda.current_stream().synchronize()
+        learner_rollout.stats = {**timer.get_all_means(), "updates": learner_policy_version, "elapsed_s": time.perf_counter() - thread_start_time,
+                                 "global_step_count": global_step_count}
         learner_rollout.final_state = learner_state
 
     return learner_rollout

@@ -260,3 +260,32 @@ def test_synthetic_env_contract():
     nx16 = torch.zeros(E, D, dtype=torch.bfloat16, device=dev)
     ops.synth_env_step(E, D, seed, 29, 0.05, 0.1, act, ob16, nx16, rew, done, trunc, rr, rl, er, el, it)
     assert torch.equal(nx16, nxt.to(torch.bfloat16)) and torch.equal(ob16, obs.to(torch.bfloat16))
+
+
+def test_optim_update_face_matches_oracle():
+    """The optax-shaped face `chain(clip_by_global_norm, adam).update(grads, state) -> (updates, state)` +
+    `apply_updates` (stoix/systems/ppo/anakin/ff_ppo.py:264-273) over the fused kernel, vs oracle.clip_adam_step:
+    five steps with a linear LR schedule, one of them clipped."""
+    from stoix_b200 import optim as optax
+    from stoix_b200.utils.training import make_learning_rate_schedule
+
+    rng = np.random.default_rng(11)
+    n = 1003  # not a multiple of 4
+    sched = make_learning_rate_schedule(3e-3, num_updates=3, num_epochs=1, num_minibatches=2)
+    opt = optax.chain(optax.clip_by_global_norm(0.5), optax.adam(sched, eps=1e-5))
+    p = torch.tensor(rng.standard_normal(n), dtype=torch.float32, device="cuda:0")
+    state = opt.init(p)
+    ref_p, ref_st = p.cpu().numpy().astype(np.float64), O.AdamState(np.zeros(n), np.zeros(n))
+    for step in range(5):
+        g = rng.standard_normal(n) * (0.2 if step == 2 else 0.005)
+        updates, state = opt.update(torch.tensor(g, dtype=torch.float32, device="cuda:0"), state, p)
+        p = optax.apply_updates(p, updates)
+        lr = O.linear_schedule(3e-3, ref_st.sched_count, 3, 1, 2)
+        ref_p, gnorm = O.clip_adam_step(ref_p, g.astype(np.float32).astype(np.float64), ref_st, lr, 0.5)
+        assert (gnorm >= 0.5) == (step == 2)
+        np.testing.assert_allclose(p.cpu().numpy(), ref_p, rtol=2e-5, atol=2e-7)
+        np.testing.assert_allclose(state.mu.cpu().numpy(), ref_st.mu, rtol=2e-5, atol=1e-9)
+        assert int(state.count.item()) == step + 1 and int(state.sched_count.item()) == step + 1
+    with pytest.raises(TypeError):
+        from stoix_b200.systems.ppo.anakin import ff_ppo
+        ff_ppo.get_learner_fn(None, (lambda p, o: None, lambda p, o: None), (opt.update, opt.update), None)
