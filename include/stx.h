@@ -41,18 +41,32 @@ extern "C" {
 #define STX_PREC_F32 0  /* fp32 CUDA-core GEMMs: the parity path (reference is fp32 everywhere) */
 #define STX_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 master weights */
 
+/* Torso activation (stoix/networks/utils.py:9-24; flax.linen functions).  STX_PREC_BF16 kernels implement RELU only. */
+#define STX_ACT_RELU 0
+#define STX_ACT_TANH 1
+#define STX_ACT_SILU 2     /* = swish */
+#define STX_ACT_ELU 3
+#define STX_ACT_GELU 4     /* nn.gelu default (tanh approximation) */
+#define STX_ACT_SIGMOID 5
+#define STX_ACT_SOFTPLUS 6
+#define STX_ACT_IDENTITY 7 /* "identity" / "none" */
+
 /*
- * One feed-forward network = MLPTorso(relu, activate_final) + Dense head
+ * One feed-forward network = MLPTorso(activation, use_layer_norm, activate_final=True) + Dense head
  * (stoix/networks/torso.py:12-33, heads.py:30-41 CategoricalHead, heads.py:129-134 ScalarCriticHead;
  * composed by FeedForwardActor / FeedForwardCritic, stoix/networks/base.py:18-59).
- * `params` is a flat fp32 arena: for layer i: W_i (sizes[i] x sizes[i+1], row-major, the flax
- * (in, out) kernel layout, y = x @ W + b) immediately followed by b_i (sizes[i+1]).
+ * `params` is a flat fp32 arena, layer after layer.  Torso layer i without LayerNorm: W_i (sizes[i] x sizes[i+1],
+ * row-major, the flax (in, out) kernel layout, y = x @ W + b) followed by b_i (sizes[i+1]).  With use_layer_norm
+ * (torso.py:26-30: Dense(use_bias=False) -> nn.LayerNorm() -> activation): W_i, LayerNorm scale_i, LayerNorm bias_i
+ * (sizes[i+1] each).  The head (last layer) is always W, b.
  */
 typedef struct StxMlp {
   int32_t n_layers;                   /* Dense layers including the head, 1..STX_MAX_LAYERS */
   int32_t sizes[STX_MAX_LAYERS + 1];  /* sizes[0] = input dim, sizes[n_layers] = head width */
   const float* params;                /* fp32 arena, stx_mlp_param_count() floats */
   const void* params_bf16;            /* bf16 shadow arena (same layout), STX_PREC_BF16 only; may be NULL for F32 */
+  int32_t activation;                 /* STX_ACT_* of the torso layers (0 = relu) */
+  int32_t use_layer_norm;             /* 1: torso layers are Dense(no bias) + LayerNorm(eps 1e-6) */
 } StxMlp;
 
 /* Hyper-parameters of _actor_loss_fn / _critic_loss_fn

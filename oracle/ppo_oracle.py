@@ -109,33 +109,81 @@ def ppo_gae_inputs(reward, done, truncated, gamma, reward_scale, dtype=np.float6
 
 @dataclass
 class MLPParams:
-    """One network: Dense(D->H0) relu ... Dense(Hk->out).  W[i] has flax layout (in, out),
-    y = x @ W + b (torso.py:24-33, heads.py:36,134)."""
+    """One network: MLPTorso(activation, use_layer_norm, activate_final=True) + Dense head (torso.py:12-33, heads.py:36,134).
+    W[i] has flax layout (in, out), y = x @ W + b.  LayerNorm torsos (torso.py:26-30): torso Dense layers have NO bias
+    (b[i] is then the LayerNorm SCALE) and ln_bias[i] is the LayerNorm bias; the head is always W, b."""
 
     W: List[np.ndarray]
     b: List[np.ndarray]
+    activation: str = "relu"
+    ln_bias: Optional[List[Optional[np.ndarray]]] = None   # None: no LayerNorm anywhere
+
+    def _like(self, W, b, ln):
+        return MLPParams(W, b, self.activation, ln)
+
+    def has_ln(self, i: int) -> bool:
+        return self.ln_bias is not None and i < len(self.W) - 1
 
     def copy(self) -> "MLPParams":
-        return MLPParams([w.copy() for w in self.W], [b.copy() for b in self.b])
+        return self._like([w.copy() for w in self.W], [b.copy() for b in self.b],
+                          None if self.ln_bias is None else [None if x is None else x.copy() for x in self.ln_bias])
 
     def astype(self, dt) -> "MLPParams":
-        return MLPParams([w.astype(dt) for w in self.W], [b.astype(dt) for b in self.b])
+        return self._like([w.astype(dt) for w in self.W], [b.astype(dt) for b in self.b],
+                          None if self.ln_bias is None else [None if x is None else x.astype(dt) for x in self.ln_bias])
 
     def flat(self) -> np.ndarray:
-        """Arena order used by the CUDA library: W0,b0,W1,b1,... each row-major."""
-        return np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(self.W, self.b)])
+        """Arena order used by the CUDA library: W0,b0,W1,b1,... each row-major (LayerNorm layers: W, scale, bias)."""
+        parts = []
+        for i, (w, b) in enumerate(zip(self.W, self.b)):
+            parts += [w.ravel(), b.ravel()]
+            if self.has_ln(i):
+                parts.append(self.ln_bias[i].ravel())
+        return np.concatenate(parts)
 
     @staticmethod
-    def from_flat(flat: np.ndarray, sizes: Sequence[int]) -> "MLPParams":
-        W, b, o = [], [], 0
-        for i in range(len(sizes) - 1):
+    def from_flat(flat: np.ndarray, sizes: Sequence[int], activation: str = "relu", use_layer_norm: bool = False) -> "MLPParams":
+        W, b, ln, o = [], [], [], 0
+        n_layers = len(sizes) - 1
+        for i in range(n_layers):
             n = sizes[i] * sizes[i + 1]
             W.append(flat[o : o + n].reshape(sizes[i], sizes[i + 1]).copy())
             o += n
             b.append(flat[o : o + sizes[i + 1]].copy())
             o += sizes[i + 1]
+            if use_layer_norm and i < n_layers - 1:
+                ln.append(flat[o : o + sizes[i + 1]].copy())
+                o += sizes[i + 1]
+            else:
+                ln.append(None)
         assert o == flat.size
-        return MLPParams(W, b)
+        return MLPParams(W, b, activation, ln if use_layer_norm else None)
+
+
+# stoix/networks/utils.py:9-24 (flax.linen functions): value and derivative w.r.t. the pre-activation
+_SQ2PI = 0.7978845608028654
+
+
+def _sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+ACTIVATIONS = {
+    "relu": (lambda z: np.maximum(z, 0.0), lambda z: (z > 0).astype(z.dtype)),
+    "tanh": (np.tanh, lambda z: 1.0 - np.tanh(z) ** 2),
+    "silu": (lambda z: z * _sigmoid(z), lambda z: _sigmoid(z) * (1.0 + z * (1.0 - _sigmoid(z)))),
+    "elu": (lambda z: np.where(z > 0, z, np.expm1(z)), lambda z: np.where(z > 0, 1.0, np.exp(z))),
+    # nn.gelu(approximate=True), the flax default
+    "gelu": (lambda z: 0.5 * z * (1.0 + np.tanh(_SQ2PI * (z + 0.044715 * z ** 3))),
+             lambda z: 0.5 * (1.0 + np.tanh(_SQ2PI * (z + 0.044715 * z ** 3)))
+             + 0.5 * z * (1.0 - np.tanh(_SQ2PI * (z + 0.044715 * z ** 3)) ** 2) * _SQ2PI * (1.0 + 3 * 0.044715 * z ** 2)),
+    "sigmoid": (_sigmoid, lambda z: _sigmoid(z) * (1.0 - _sigmoid(z))),
+    "softplus": (lambda z: np.logaddexp(z, 0.0), _sigmoid),
+    "identity": (lambda z: z, lambda z: np.ones_like(z)),
+}
+ACTIVATIONS["swish"] = ACTIVATIONS["silu"]
+ACTIVATIONS["none"] = ACTIVATIONS["identity"]
+LN_EPS = 1e-6  # flax nn.LayerNorm default epsilon
 
 
 def orthogonal_init(rng: np.random.Generator, shape, scale: float) -> np.ndarray:
@@ -172,38 +220,75 @@ def _bf16_round(x: np.ndarray) -> np.ndarray:
 
 
 def mlp_forward(p: MLPParams, x: np.ndarray, bf16_operands: bool = False):
-    """MLPTorso (relu, activate_final=True, no layer norm) followed by a Dense head.
-    Returns (out, cache) where cache holds the layer inputs for the backward pass.
+    """MLPTorso (activate_final=True) followed by a Dense head.  Returns (out, cache); cache[i] is the INPUT of layer i
+    (what the backward pass multiplies dY with); for LayerNorm / non-relu torsos the cache also carries the
+    pre-activations (`cache.pre[i]`: Dense output of torso layer i, `cache.stats[i]`: its per-row (mean, rstd)).
 
-    ``bf16_operands=True`` emulates the tensor-core path: every GEMM operand (activations and
-    weights) is rounded to bf16, products/accumulation stay in the working precision."""
+    ``bf16_operands=True`` emulates the tensor-core path (relu, no LayerNorm only): every GEMM operand (activations
+    and weights) is rounded to bf16, products/accumulation stay in the working precision."""
     rnd = _bf16_round if bf16_operands else (lambda a: a)
-    acts = [rnd(x)]
+    f, _ = ACTIVATIONS[p.activation]
+    acts = _Cache([rnd(x)])
     h = acts[0]
     n = len(p.W)
     for i in range(n):
-        z = h @ rnd(p.W[i]) + p.b[i]
+        if i < n - 1 and p.has_ln(i):
+            assert not bf16_operands, "the bf16 emulation covers the relu / no-LayerNorm networks of the tcgen05 path"
+            u = h @ p.W[i]                                          # Dense(use_bias=False), torso.py:26
+            mean = u.mean(axis=-1, keepdims=True)
+            rstd = 1.0 / np.sqrt(((u - mean) ** 2).mean(axis=-1, keepdims=True) + LN_EPS)
+            z = (u - mean) * rstd * p.b[i] + p.ln_bias[i]           # nn.LayerNorm(): scale, bias
+            acts.pre.append(u), acts.stats.append((mean, rstd))
+        else:
+            z = h @ rnd(p.W[i]) + p.b[i]
+            acts.pre.append(z), acts.stats.append(None)
         if i < n - 1:
-            h = rnd(np.maximum(z, 0.0))  # nn.relu
+            h = rnd(f(z))
             acts.append(h)
         else:
             out = z
     return out, acts
 
 
+class _Cache(list):
+    """list of layer inputs (what the existing callers index) + pre-activations / LayerNorm statistics."""
+
+    def __init__(self, items):
+        super().__init__(items)
+        self.pre, self.stats = [], []
+
+
 def mlp_backward(p: MLPParams, acts, dout: np.ndarray, bf16_operands: bool = False) -> MLPParams:
-    """Manual reverse-mode of mlp_forward: grads wrt W[i], b[i] given d(loss)/d(out)."""
+    """Manual reverse-mode of mlp_forward: grads wrt W[i], b[i] (LayerNorm layers: scale in b[i], bias in ln_bias[i])
+    given d(loss)/d(out)."""
     rnd = _bf16_round if bf16_operands else (lambda a: a)
+    _, fp = ACTIVATIONS[p.activation]
     n = len(p.W)
     gW, gb = [None] * n, [None] * n
-    d = dout
+    gln = [None] * n
+    d = dout   # gradient w.r.t. the Dense output of layer i
     for i in range(n - 1, -1, -1):
         dr = rnd(d)
         gW[i] = acts[i].T @ dr
-        gb[i] = d.sum(axis=0)
+        if p.has_ln(i):
+            gb[i], gln[i] = d_scale, d_lnbias   # computed when stepping through layer i's LayerNorm below (from layer i+1)
+        else:
+            gb[i] = d.sum(axis=0)
         if i > 0:
-            d = (dr @ rnd(p.W[i]).T) * (acts[i] > 0)
-    return MLPParams(gW, gb)
+            dh = dr @ rnd(p.W[i]).T                                  # w.r.t. h_{i-1} = f(z_{i-1})
+            j = i - 1
+            if p.has_ln(j):
+                u, (mean, rstd) = acts.pre[j], acts.stats[j]
+                uh = (u - mean) * rstd
+                dz = dh * fp(uh * p.b[j] + p.ln_bias[j])
+                d_scale, d_lnbias = (dz * uh).sum(axis=0), dz.sum(axis=0)
+                dhat = dz * p.b[j]
+                d = rstd * (dhat - dhat.mean(axis=-1, keepdims=True) - uh * (dhat * uh).mean(axis=-1, keepdims=True))
+            elif p.activation == "relu":
+                d = dh * (acts[i] > 0)                               # identical to f'(z) for relu; keeps the bf16 path's form
+            else:
+                d = dh * fp(acts.pre[j])
+    return MLPParams(gW, gb, p.activation, gln if p.ln_bias is not None else None)
 
 
 def log_softmax(z: np.ndarray) -> np.ndarray:
@@ -432,8 +517,8 @@ def ppo_update(
             c_lr = linear_schedule(h.critic_lr, c_state.sched_count, h.num_updates, h.epochs, h.num_minibatches, h.decay_learning_rates)
             a_new, _ = clip_adam_step(actor.flat(), a_g.astype(dt), a_state, a_lr, h.max_grad_norm)
             c_new, _ = clip_adam_step(critic.flat(), c_g.astype(dt), c_state, c_lr, h.max_grad_norm)
-            actor = MLPParams.from_flat(a_new, sizes_a)
-            critic = MLPParams.from_flat(c_new, sizes_c)
+            actor = MLPParams.from_flat(a_new, sizes_a, actor.activation, actor.ln_bias is not None)
+            critic = MLPParams.from_flat(c_new, sizes_c, critic.activation, critic.ln_bias is not None)
             for k in metrics:
                 metrics[k][ep, i] = info[k]
     return actor, critic, metrics, adv, targets

@@ -23,7 +23,12 @@ class StxMlp(C.Structure):
         ("sizes", C.c_int32 * (STX_MAX_LAYERS + 1)),
         ("params", C.c_void_p),
         ("params_bf16", C.c_void_p),
+        ("activation", C.c_int32),
+        ("use_layer_norm", C.c_int32),
     ]
+
+
+STX_ACTIVATIONS = {"relu": 0, "tanh": 1, "silu": 2, "swish": 2, "elu": 3, "gelu": 4, "sigmoid": 5, "softplus": 6, "identity": 7, "none": 7}
 
 
 class StxPpoHyper(C.Structure):

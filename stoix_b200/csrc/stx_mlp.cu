@@ -26,8 +26,14 @@ int check_mlp(const StxMlp* m, const char* who) {
   for (int i = 0; i <= m->n_layers; ++i)
     STX_REQUIRE(m->sizes[i] > 0, STX_E_SHAPE, "%s: sizes[%d]=%d", who, i, m->sizes[i]);
   STX_REQUIRE(m->params != nullptr, STX_E_ARG, "%s: null params", who);
+  STX_REQUIRE(m->activation >= STX_ACT_RELU && m->activation <= STX_ACT_IDENTITY, STX_E_ARG, "%s: activation=%d", who, m->activation);
+  if (m->use_layer_norm)
+    for (int i = 1; i < m->n_layers; ++i)
+      STX_REQUIRE(m->sizes[i] <= 32 * simt::kLnMaxCols, STX_E_SHAPE, "%s: LayerNorm width %d > %d", who, m->sizes[i], 32 * simt::kLnMaxCols);
   return STX_OK;
 }
+
+inline bool layer_has_ln(const StxMlp* m, int i) { return m->use_layer_norm && i < m->n_layers - 1; }
 
 int max_width(const StxMlp* m) {
   int w = 0;
@@ -35,21 +41,31 @@ int max_width(const StxMlp* m) {
   return w;
 }
 
-// offsets of W_i and b_i inside a network arena
+// offsets of W_i and b_i inside a network arena; LayerNorm torso layers: boff = LayerNorm scale, +sizes[i+1] = LayerNorm bias
 void layer_offsets(const StxMlp* m, int64_t* woff, int64_t* boff) {
   int64_t o = 0;
   for (int i = 0; i < m->n_layers; ++i) {
     woff[i] = o;
     o += (int64_t)m->sizes[i] * m->sizes[i + 1];
     boff[i] = o;
-    o += m->sizes[i + 1];
+    o += (layer_has_ln(m, i) ? 2 : 1) * (int64_t)m->sizes[i + 1];
   }
 }
 
-// Forward through all layers.  acts[i] (i=1..n-1) receive hidden activations (M x sizes[i]);
-// the head output goes to `out`.  x may be gathered through row_idx.
+// operand transform of the GEMM that consumes the output of torso layer `prev` (see stx_simt_gemm.cuh)
+void set_operand_transform(simt::GemmArgs& g, const StxMlp* m, int prev, const int64_t* boff, float* const* stats) {
+  g.a_act = m->activation;
+  if (layer_has_ln(m, prev)) {
+    g.a_stats = stats[prev + 1];
+    g.a_gamma = m->params + boff[prev];
+    g.a_beta = m->params + boff[prev] + m->sizes[prev + 1];
+  }
+}
+
+// Forward through all layers.  acts[i] (i=1..n-1) receive the PRE-activation Dense outputs U_i (M x sizes[i]), stats[i]
+// (LayerNorm torsos) their per-row (mean, rstd); the head output goes to `out`.  x may be gathered through row_idx.
 int simt_forward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M,
-                 float* const* acts, float* out, cudaStream_t st) {
+                 float* const* acts, float* const* stats, float* out, cudaStream_t st) {
   int64_t woff[STX_MAX_LAYERS], boff[STX_MAX_LAYERS];
   layer_offsets(m, woff, boff);
   const float* in = x;
@@ -59,13 +75,19 @@ int simt_forward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* ro
     const bool last = (i == m->n_layers - 1);
     simt::GemmArgs g{};
     g.A = in, g.lda = ld, g.rowidx = ridx;
-    g.B = m->params + woff[i], g.bias = m->params + boff[i];
+    g.a_act = -1, g.mask_act = -1;
+    if (i > 0) set_operand_transform(g, m, i - 1, boff, stats);  // MLPTorso activate_final=True: the head sees f(.) too
+    g.B = m->params + woff[i];
+    g.bias = layer_has_ln(m, i) ? nullptr : m->params + boff[i];  // torso.py:26: use_bias = not use_layer_norm
     g.C = last ? out : acts[i + 1];
     g.M = M, g.N = m->sizes[i + 1], g.K = m->sizes[i];
-    g.relu = last ? 0 : 1;  // MLPTorso activate_final=True; the head Dense has no activation
     dim3 grid((g.N + simt::BN - 1) / simt::BN, (unsigned)((M + simt::BM - 1) / simt::BM));
     simt::gemm_kernel<simt::FWD><<<grid, simt::kThreads, 0, st>>>(g);
     STX_LAUNCH_OK();
+    if (layer_has_ln(m, i)) {
+      simt::ln_stats_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(acts[i + 1], M, g.N, stats[i + 1]);
+      STX_LAUNCH_OK();
+    }
     in = g.C, ld = g.N, ridx = nullptr;
   }
   return STX_OK;
@@ -118,7 +140,10 @@ __global__ void categorical_kernel(const float* __restrict__ logits, int64_t E, 
 
 // ---- fp32 PPO minibatch: workspace carving -------------------------------------------------
 struct SimtPpoWs {
-  float* acts[STX_MAX_LAYERS + 1];  // hidden activations, index 1..n-1
+  float* acts[STX_MAX_LAYERS + 1];  // pre-activation Dense outputs of the torso layers, index 1..n-1
+  float* stats[STX_MAX_LAYERS + 1]; // LayerNorm torsos: per-row (mean, rstd) of acts[i]
+  float* ln_part;                   // LayerNorm backward: [blocks][2 * width] column-sum partials
+  int ln_blocks, ln_rows;
   float* head;                      // logits or value (mb x head)
   float* dhead;                     // d logits / d value
   float* dbuf[2];                   // ping-pong d(hidden)
@@ -148,6 +173,10 @@ SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
   w.counter = reinterpret_cast<unsigned int*>(take(256));
   const int mw = max_width(m);
   for (int i = 1; i < m->n_layers; ++i) w.acts[i] = reinterpret_cast<float*>(take((size_t)mb * m->sizes[i] * 4));
+  for (int i = 1; i < m->n_layers; ++i) w.stats[i] = m->use_layer_norm ? reinterpret_cast<float*>(take((size_t)mb * 2 * 4)) : nullptr;
+  w.ln_rows = 128;  // rows per block of ln_backward_kernel
+  w.ln_blocks = (int)((mb + w.ln_rows - 1) / w.ln_rows);
+  w.ln_part = m->use_layer_norm ? reinterpret_cast<float*>(take((size_t)w.ln_blocks * 2 * mw * 4)) : nullptr;
   w.head = reinterpret_cast<float*>(take((size_t)mb * m->sizes[m->n_layers] * 4));
   w.dhead = reinterpret_cast<float*>(take((size_t)mb * m->sizes[m->n_layers] * 4));
   w.dbuf[0] = reinterpret_cast<float*>(take((size_t)mb * mw * 4));
@@ -170,14 +199,16 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
   int pp = 0;
   for (int i = m->n_layers - 1; i >= 0; --i) {
     const int nin = m->sizes[i], nout = m->sizes[i + 1];
-    // dW_i, db_i partials: input of layer i is x (gathered) for i==0 else acts[i]
+    // dW_i, db_i partials: input of layer i is x (gathered) for i==0 else f(acts[i]) / f(LN(acts[i])) rebuilt on load
     simt::GemmArgs g{};
     g.A = (i == 0) ? x : ws.acts[i];
     g.lda = (i == 0) ? ldx : nin;
     g.rowidx = (i == 0) ? row_idx : nullptr;
+    g.a_act = -1, g.mask_act = -1;
+    if (i > 0) set_operand_transform(g, m, i - 1, boff, ws.stats);
     g.B = dY;
     g.C = ws.partials + woff[i];
-    g.dbias = ws.partials + boff[i];
+    g.dbias = layer_has_ln(m, i) ? nullptr : ws.partials + boff[i];  // LayerNorm layers: Dense has no bias (scale / bias below)
     g.M = mb, g.N = nout, g.K = nin;
     g.rows_per_split = rows_per_split;
     g.part_stride = np, g.dbias_stride = np;
@@ -185,22 +216,40 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
     simt::gemm_kernel<simt::DW><<<grid, simt::kThreads, 0, st>>>(g);
     STX_LAUNCH_OK();
     if (i > 0) {
-      // d(acts[i]) = (dY @ W_i^T) * relu'(acts[i])
+      // d(U_{i-1}) from dY: through the Dense (dY @ W_i^T), the activation and, for LayerNorm torsos, the normalisation
+      const bool ln = layer_has_ln(m, i - 1);
       simt::GemmArgs d{};
       d.A = dY, d.lda = nout;
+      d.a_act = -1;
       d.B = m->params + woff[i];
       d.C = ws.dbuf[pp];
-      d.mask = ws.acts[i];
+      d.mask = ln ? nullptr : ws.acts[i];
+      d.mask_act = ln ? -1 : m->activation;
       d.M = mb, d.N = nin, d.K = nout;
       dim3 gd((nin + simt::BN - 1) / simt::BN, (unsigned)((mb + simt::BM - 1) / simt::BM));
       simt::gemm_kernel<simt::DX><<<gd, simt::kThreads, 0, st>>>(d);
       STX_LAUNCH_OK();
+      if (ln) {
+        const float* gamma = m->params + boff[i - 1];
+        simt::ln_backward_kernel<<<ws.ln_blocks, 32 * simt::kLnWarps, sizeof(float) * simt::kLnWarps * 2 * nin, st>>>(
+            ws.dbuf[pp], ws.acts[i], ws.stats[i], gamma, gamma + nin, m->activation, mb, nin, ws.ln_rows, ws.ln_part);
+        STX_LAUNCH_OK();
+        // d(scale | bias) of layer i-1: fixed-order sum over the blocks, straight into the gradient arena
+        simt::reduce_partials_kernel<<<(unsigned)((2 * nin + 255) / 256), 256, 0, st>>>(ws.ln_part, ws.ln_blocks, 2 * (int64_t)nin, 2 * (int64_t)nin,
+                                                                                        grad_weight, net_grad + boff[i - 1], overwrite);
+        STX_LAUNCH_OK();
+      }
       dY = ws.dbuf[pp];
       pp ^= 1;
     }
   }
-  simt::reduce_partials_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ws.partials, ws.splits, np, np, grad_weight, net_grad, overwrite);
-  STX_LAUNCH_OK();
+  // fixed-order sum of the split-M partials: W_i and, for layers with a Dense bias, b_i (LayerNorm scale / bias were reduced above)
+  for (int i = 0; i < m->n_layers; ++i) {
+    const int64_t n = (int64_t)m->sizes[i] * m->sizes[i + 1] + (layer_has_ln(m, i) ? 0 : m->sizes[i + 1]);
+    simt::reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.partials + woff[i], ws.splits, np, n, grad_weight,
+                                                                              net_grad + woff[i], overwrite);
+    STX_LAUNCH_OK();
+  }
   return STX_OK;
 }
 
@@ -212,7 +261,8 @@ using namespace stx;
 extern "C" int64_t stx_mlp_param_count(const StxMlp* m) {
   if (!m) return 0;
   int64_t o = 0;
-  for (int i = 0; i < m->n_layers; ++i) o += (int64_t)m->sizes[i] * m->sizes[i + 1] + m->sizes[i + 1];
+  for (int i = 0; i < m->n_layers; ++i)
+    o += (int64_t)m->sizes[i] * m->sizes[i + 1] + ((m->use_layer_norm && i < m->n_layers - 1) ? 2 : 1) * (int64_t)m->sizes[i + 1];
   return o;
 }
 
@@ -220,7 +270,7 @@ extern "C" size_t stx_mlp_forward_workspace_bytes(const StxMlp* m, int64_t M, in
   if (!m || M <= 0) return 0;
   if (precision == STX_PREC_BF16) return tc_mlp_forward_workspace_bytes(m, M);
   size_t o = 0;
-  for (int i = 1; i < m->n_layers; ++i) o += align_up((size_t)M * m->sizes[i] * 4);
+  for (int i = 1; i < m->n_layers; ++i) o += align_up((size_t)M * m->sizes[i] * 4) + (m->use_layer_norm ? align_up((size_t)M * 8) : 0);
   return o > 0 ? o : 256;
 }
 
@@ -236,12 +286,17 @@ extern "C" int stx_mlp_forward(const StxMlp* m, const void* x, int64_t ldx, cons
     return tc_mlp_forward(m, x, ldx, row_idx, M, out, workspace, workspace_bytes, (cudaStream_t)stream);
   STX_REQUIRE(precision == STX_PREC_F32, STX_E_UNSUPPORTED, "stx_mlp_forward: precision=%d", precision);
   float* acts[STX_MAX_LAYERS + 1] = {nullptr};
+  float* stats[STX_MAX_LAYERS + 1] = {nullptr};
   char* p = reinterpret_cast<char*>(workspace);
   for (int i = 1; i < m->n_layers; ++i) {
     acts[i] = reinterpret_cast<float*>(p);
     p += align_up((size_t)M * m->sizes[i] * 4);
+    if (m->use_layer_norm) {
+      stats[i] = reinterpret_cast<float*>(p);
+      p += align_up((size_t)M * 8);
+    }
   }
-  return simt_forward(m, reinterpret_cast<const float*>(x), ldx, row_idx, M, acts, out, (cudaStream_t)stream);
+  return simt_forward(m, reinterpret_cast<const float*>(x), ldx, row_idx, M, acts, stats, out, (cudaStream_t)stream);
 }
 
 extern "C" int stx_categorical(const float* logits, int64_t E, int A, int sample, uint64_t seed,
@@ -332,7 +387,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
   // ---- actor: forward, loss, backward (ff_ppo.py:191-213, 238-241) ----
   {
     SimtPpoWs ws = carve(actor, mb, reinterpret_cast<char*>(workspace));
-    if (int rc = simt_forward(actor, x, D, idx, mb, ws.acts, ws.head, st)) return rc;
+    if (int rc = simt_forward(actor, x, D, idx, mb, ws.acts, ws.stats, ws.head, st)) return rc;
     LossArgs g{};
     g.logits = ws.head, g.value = nullptr, g.idx = idx, g.row0 = mb_off;
     g.action = b->action, g.logp_old = b->log_prob, g.v_old = b->value, g.adv = b->advantages, g.tgt = b->targets;
@@ -346,7 +401,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
   // ---- critic: forward, loss, backward (ff_ppo.py:215-235, 244-247) ----
   {
     SimtPpoWs ws = carve(critic, mb, reinterpret_cast<char*>(workspace));
-    if (int rc = simt_forward(critic, x, D, idx, mb, ws.acts, ws.head, st)) return rc;
+    if (int rc = simt_forward(critic, x, D, idx, mb, ws.acts, ws.stats, ws.head, st)) return rc;
     LossArgs g{};
     g.logits = nullptr, g.value = ws.head, g.value_ld = 1, g.idx = idx, g.row0 = mb_off;
     g.action = b->action, g.logp_old = b->log_prob, g.v_old = b->value, g.adv = b->advantages, g.tgt = b->targets;

@@ -328,13 +328,13 @@ static int g_forward_ctas = 0;  // stx_tc_set_forward_ctas: grid cap of the pers
 
 static bool tc_shape_ok(const StxMlp* m) {
   return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
-         m->sizes[3] >= 1 && m->sizes[3] <= 16;
+         m->sizes[3] >= 1 && m->sizes[3] <= 16 && m->activation == STX_ACT_RELU && !m->use_layer_norm;
 }
 
 int tc_forward_impl(const StxMlp* m, const void* x, int64_t ldx, int64_t M, float* out, float* dbg_h1, float* dbg_h2,
                     cudaStream_t st) {
   STX_REQUIRE(tc_shape_ok(m), STX_E_SHAPE,
-              "STX_PREC_BF16 MLP kernels need sizes [D<=64 (mult of 8), 256, 256, head<=16]; got %d layers [%d,%d,%d,%d]",
+              "STX_PREC_BF16 MLP kernels need a relu torso without LayerNorm and sizes [D<=64 (mult of 8), 256, 256, head<=16]; got %d layers [%d,%d,%d,%d]",
               m->n_layers, m->sizes[0], m->sizes[1], m->sizes[2], m->sizes[3]);
   STX_REQUIRE(m->params_bf16 != nullptr, STX_E_ARG, "STX_PREC_BF16 needs StxMlp.params_bf16 (bf16 shadow of the arena)");
   const int D = m->sizes[0], A = m->sizes[3];

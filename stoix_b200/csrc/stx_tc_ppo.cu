@@ -1205,7 +1205,7 @@ TcWs carve_tc(int64_t mb, char* base) {
 
 bool tc_ppo_shape_ok(const StxMlp* m) {
   return m->n_layers == 3 && m->sizes[1] == kH && m->sizes[2] == kH && m->sizes[0] <= 64 && m->sizes[0] % 8 == 0 &&
-         m->sizes[3] >= 1 && m->sizes[3] <= 16;
+         m->sizes[3] >= 1 && m->sizes[3] <= 16 && m->activation == STX_ACT_RELU && !m->use_layer_norm;
 }
 
 // max dynamic shared memory opt-in, once per device and kernel
@@ -1232,7 +1232,7 @@ int tc_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic, const StxP
                            cudaStream_t st, const StxFusedAdam* opt) {
   using namespace tc;
   STX_REQUIRE(tc_ppo_shape_ok(actor) && tc_ppo_shape_ok(critic), STX_E_SHAPE,
-              "STX_PREC_BF16 PPO kernels need MLP [D<=64 (mult of 8), 256, 256, head<=16]");
+              "STX_PREC_BF16 PPO kernels need a relu MLP without LayerNorm, sizes [D<=64 (mult of 8), 256, 256, head<=16]");
   STX_REQUIRE(mb % 128 == 0, STX_E_SHAPE, "STX_PREC_BF16 PPO kernels need a minibatch that is a multiple of 128 rows (got %lld)", (long long)mb);
   STX_REQUIRE(actor->params_bf16 && critic->params_bf16, STX_E_ARG, "STX_PREC_BF16 needs the bf16 shadow arenas");
   const int D = actor->sizes[0];

@@ -397,7 +397,8 @@ extern "C" int stx_tc_rollout_synth(const StxMlp* actor, void* obs, void* next_o
                   is_terminal && run_return && run_length,
               STX_E_ARG, "stx_tc_rollout_synth: null pointer");
   STX_REQUIRE(actor->n_layers == 3 && actor->sizes[1] == 256 && actor->sizes[2] == 256 && actor->sizes[0] <= 64 &&
-                  actor->sizes[0] % 8 == 0 && actor->sizes[3] >= 1 && actor->sizes[3] <= 16,
+                  actor->sizes[0] % 8 == 0 && actor->sizes[3] >= 1 && actor->sizes[3] <= 16 && actor->activation == STX_ACT_RELU &&
+                  !actor->use_layer_norm,
               STX_E_SHAPE, "stx_tc_rollout_synth: actor must be MLP [D<=64 (mult of 8), 256, 256, A<=16]");
   STX_REQUIRE(E > 0 && E % 128 == 0 && T > 0, STX_E_SHAPE, "stx_tc_rollout_synth: num_envs (%lld) must be a multiple of 128", (long long)E);
   STX_REQUIRE(actor->params_bf16 != nullptr, STX_E_ARG, "stx_tc_rollout_synth needs the bf16 shadow arena");

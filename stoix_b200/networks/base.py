@@ -42,6 +42,9 @@ def build_param_tree(spec: ops.MlpSpec, flat: torch.Tensor, head_name: str, flat
     for i in range(n - 1):
         torso[f"Dense_{i}"] = {"kernel": flat[sl[i][0]].view(spec.sizes[i], spec.sizes[i + 1]), "bias": flat[sl[i][1]]}
     head = {"Dense_0": {"kernel": flat[sl[n - 1][0]].view(spec.sizes[n - 1], spec.sizes[n]), "bias": flat[sl[n - 1][1]]}}
+    for i, b in enumerate(spec.ln_bias_slices()):  # LayerNorm torsos: Dense_i has no bias; LayerNorm_i/{scale, bias} (flax auto-names)
+        if b is not None:
+            torso[f"LayerNorm_{i}"] = {"scale": torso[f"Dense_{i}"].pop("bias"), "bias": flat[b]}
     tree = ParamTree({"params": {"torso": torso, head_name: head}})
     tree.flat = flat[: spec.param_count]
     tree.spec = spec
@@ -59,7 +62,8 @@ class _FeedForward:
         self.precision = ops.STX_PREC_F32
 
     def spec_for(self, obs_dim: int) -> ops.MlpSpec:
-        return ops.MlpSpec(tuple([int(obs_dim), *self.torso.layer_sizes, int(self.head.out_dim)]))
+        return ops.MlpSpec(tuple([int(obs_dim), *self.torso.layer_sizes, int(self.head.out_dim)]), activation=self.torso.activation,
+                           use_layer_norm=self.torso.use_layer_norm)
 
     def init(self, key, x: torch.Tensor, flat: Optional[torch.Tensor] = None) -> ParamTree:
         """Initialise parameters (orthogonal kernels, zero biases -- torso.py:18, heads.py:32,130).
@@ -76,6 +80,8 @@ class _FeedForward:
         for i in range(spec.n_layers):
             scale = self.torso.kernel_init_scale if i < spec.n_layers - 1 else self.head.kernel_init_scale
             host[sl[i][0]] = _orthogonal(gen, spec.sizes[i], spec.sizes[i + 1], scale).reshape(-1)
+            if spec.has_ln(i):
+                host[sl[i][1]] = 1.0  # LayerNorm scale = ones, bias = zeros (flax defaults)
         if flat is None:
             flat = torch.zeros(spec.param_count, dtype=torch.float32, device=device)
         flat[: spec.param_count].copy_(host)

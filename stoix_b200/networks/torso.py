@@ -14,13 +14,11 @@ from .utils import parse_activation_fn
 class MLPTorso:
     def __init__(self, layer_sizes: Sequence[int], activation: str = "relu", use_layer_norm: bool = False,
                  kernel_init: Optional[float] = None, activate_final: bool = True):
-        if use_layer_norm:
-            raise NotImplementedError("use_layer_norm=True is outside the B200 hot path (mlp.yaml default is False)")
         if not activate_final:
-            raise NotImplementedError("activate_final=False is outside the B200 hot path")
+            raise NotImplementedError("MLPTorso(activate_final=False) is not built (every PPO network config activates the last torso layer)")
         self.layer_sizes = tuple(int(s) for s in layer_sizes)
         self.activation = parse_activation_fn(activation)
-        self.use_layer_norm = False
+        self.use_layer_norm = bool(use_layer_norm)   # Dense(use_bias=False) -> LayerNorm -> activation (torso.py:26-32)
         self.activate_final = True
         # orthogonal(sqrt(2)) is the reference default (torso.py:18)
         self.kernel_init_scale = float(np.sqrt(2.0)) if kernel_init is None else float(kernel_init)

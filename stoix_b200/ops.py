@@ -59,37 +59,58 @@ def _zeros_scratch(key: Tuple, nbytes: int, device) -> torch.Tensor:
 
 @dataclass(frozen=True)
 class MlpSpec:
-    """Layer widths of one network: sizes[0] = input dim, sizes[-1] = head width."""
+    """Layer widths of one network: sizes[0] = input dim, sizes[-1] = head width; torso activation and LayerNorm switch
+    (stoix/networks/torso.py:12-33).  Arena layout per layer: W (in x out), then b (out) -- or, for LayerNorm torso
+    layers, LayerNorm scale (out) and LayerNorm bias (out), the Dense having no bias (torso.py:26)."""
 
     sizes: Tuple[int, ...]
+    activation: str = "relu"
+    use_layer_norm: bool = False
 
     @property
     def n_layers(self) -> int:
         return len(self.sizes) - 1
 
+    def has_ln(self, i: int) -> bool:
+        return self.use_layer_norm and i < self.n_layers - 1
+
     @property
     def param_count(self) -> int:
-        return sum(self.sizes[i] * self.sizes[i + 1] + self.sizes[i + 1] for i in range(self.n_layers))
+        return sum(self.sizes[i] * self.sizes[i + 1] + (2 if self.has_ln(i) else 1) * self.sizes[i + 1] for i in range(self.n_layers))
 
     def layer_slices(self) -> List[Tuple[slice, slice]]:
+        """(kernel slice, bias slice) per layer; for LayerNorm torso layers the second slice is the LayerNorm SCALE and
+        `ln_bias_slices()[i]` the LayerNorm bias."""
         out, o = [], 0
         for i in range(self.n_layers):
-            nw = self.sizes[i] * self.sizes[i + 1]
-            out.append((slice(o, o + nw), slice(o + nw, o + nw + self.sizes[i + 1])))
-            o += nw + self.sizes[i + 1]
+            nw, nb = self.sizes[i] * self.sizes[i + 1], self.sizes[i + 1]
+            out.append((slice(o, o + nw), slice(o + nw, o + nw + nb)))
+            o += nw + (2 if self.has_ln(i) else 1) * nb
         return out
+
+    def ln_bias_slices(self) -> List[Optional[slice]]:
+        sl = self.layer_slices()
+        return [slice(sl[i][1].stop, sl[i][1].stop + self.sizes[i + 1]) if self.has_ln(i) else None for i in range(self.n_layers)]
 
     def c_struct(self, params: torch.Tensor, params_bf16: Optional[torch.Tensor] = None) -> _lib.StxMlp:
         if self.n_layers < 1 or self.n_layers > _lib.STX_MAX_LAYERS:
             raise StxError(f"MLP with {self.n_layers} Dense layers unsupported (max {_lib.STX_MAX_LAYERS})")
         if params.dtype != torch.float32 or params.numel() < self.param_count:
             raise StxError("parameter arena must be float32 with at least param_count elements")
+        m = self.shape_struct()
+        m.params = params.data_ptr()
+        m.params_bf16 = params_bf16.data_ptr() if params_bf16 is not None else None
+        return m
+
+    def shape_struct(self) -> _lib.StxMlp:
+        if self.activation not in _lib.STX_ACTIVATIONS:
+            raise StxError(f"activation '{self.activation}' has no kernel implementation")
         m = _lib.StxMlp()
         m.n_layers = self.n_layers
         for i, s in enumerate(self.sizes):
             m.sizes[i] = int(s)
-        m.params = params.data_ptr()
-        m.params_bf16 = params_bf16.data_ptr() if params_bf16 is not None else None
+        m.activation = _lib.STX_ACTIVATIONS[self.activation]
+        m.use_layer_norm = int(bool(self.use_layer_norm))
         return m
 
 
@@ -266,10 +287,7 @@ class PpoBatch:
 
 
 def _shape_only_struct(spec: MlpSpec) -> _lib.StxMlp:
-    m = _lib.StxMlp()
-    m.n_layers = spec.n_layers
-    for i, s in enumerate(spec.sizes):
-        m.sizes[i] = int(s)
+    m = spec.shape_struct()
     m.params = 256  # never dereferenced by the *_bytes queries
     m.params_bf16 = None
     return m

@@ -40,7 +40,7 @@ def test_binding_matches_header():
 def test_struct_layouts_match_c():
     from stoix_b200 import _lib
 
-    assert ctypes.sizeof(_lib.StxMlp) == 4 + 5 * 4 + 8 + 8
+    assert ctypes.sizeof(_lib.StxMlp) == 4 + 5 * 4 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.StxAdamSeg) == 24
     assert ctypes.sizeof(_lib.StxAdamHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoHyper) == 32

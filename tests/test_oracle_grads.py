@@ -3,6 +3,7 @@
 CPU in float64, restating the reference's loss code (stoix/utils/loss.py:17-32,68-78;
 ff_ppo.py:191-235) with torch ops."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import ppo_oracle as O
@@ -129,3 +130,38 @@ def test_derive_shapes():
     # total_timestep_checker.py:57-61,88-96,104-131 with the default config values
     assert O.derive_shapes(1024, 1, 1, 1e7, 128, 20) == (1024, 76, 3)
     assert O.derive_shapes(4096 * 8, 8, 1, 4096 * 8 * 128 * 10, 128, 5) == (4096, 10, 2)
+
+
+@pytest.mark.parametrize("use_layer_norm", [False, True])
+@pytest.mark.parametrize("activation", ["relu", "tanh", "silu", "elu", "gelu", "sigmoid", "softplus", "identity"])
+def test_torso_options_forward_backward_match_autograd(activation, use_layer_norm):
+    """MLPTorso(activation, use_layer_norm) of stoix/networks/torso.py:24-33 (flax Dense / LayerNorm(eps 1e-6) /
+    nn.<activation>, gelu in its default tanh approximation): the oracle's forward and hand-derived backward against
+    torch.nn.functional + autograd in float64."""
+    F = torch.nn.functional
+    acts_t = {"relu": torch.relu, "tanh": torch.tanh, "silu": F.silu, "elu": F.elu, "gelu": lambda z: F.gelu(z, approximate="tanh"),
+              "sigmoid": torch.sigmoid, "softplus": F.softplus, "identity": lambda z: z}
+    rng = np.random.default_rng(len(activation) + int(use_layer_norm))
+    sizes = [6, 16, 16, 3]
+    W = [rng.standard_normal((sizes[i], sizes[i + 1])) * 0.5 for i in range(3)]
+    b = [rng.standard_normal(sizes[i + 1]) * 0.3 + (1.0 if use_layer_norm and i < 2 else 0.0) for i in range(3)]
+    lnb = [rng.standard_normal(sizes[i + 1]) * 0.3 if i < 2 else None for i in range(3)] if use_layer_norm else None
+    p = O.MLPParams(W, b, activation, lnb)
+    assert np.array_equal(O.MLPParams.from_flat(p.flat(), sizes, activation, use_layer_norm).flat(), p.flat())
+    x, dout = rng.standard_normal((9, 6)), rng.standard_normal((9, 3))
+    out, cache = O.mlp_forward(p, x)
+    g = O.mlp_backward(p, cache, dout)
+    Wt = [torch.tensor(w, requires_grad=True) for w in W]
+    bt = [torch.tensor(v, requires_grad=True) for v in b]
+    lt = [torch.tensor(v, requires_grad=True) if v is not None else None for v in (lnb or [None] * 3)]
+    h = torch.tensor(x)
+    for i in range(3):
+        z = F.layer_norm(h @ Wt[i], (sizes[i + 1],), bt[i], lt[i], eps=1e-6) if (use_layer_norm and i < 2) else h @ Wt[i] + bt[i]
+        h = acts_t[activation](z) if i < 2 else z
+    (h * torch.tensor(dout)).sum().backward()
+    np.testing.assert_allclose(out, h.detach().numpy(), rtol=1e-12, atol=1e-12)
+    for i in range(3):
+        np.testing.assert_allclose(g.W[i], Wt[i].grad.numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(g.b[i], bt[i].grad.numpy(), rtol=1e-10, atol=1e-12)
+        if use_layer_norm and i < 2:
+            np.testing.assert_allclose(g.ln_bias[i], lt[i].grad.numpy(), rtol=1e-10, atol=1e-12)
