@@ -35,7 +35,7 @@ extern "C" {
 #define STX_E_UNSUPPORTED (-4)
 #define STX_E_WORKSPACE (-5) /* workspace too small */
 
-#define STX_MAX_LAYERS 4 /* Dense layers per network (hidden layers + head) */
+#define STX_MAX_LAYERS 7 /* Dense layers per network (hidden layers + head) */
 
 /* Compute precision of the MLP GEMMs. */
 #define STX_PREC_F32 0  /* fp32 CUDA-core GEMMs: the parity path (reference is fp32 everywhere) */
@@ -326,6 +326,78 @@ int stx_running_stats_finalize(const double* sums, int D, int64_t* count, float*
                                float std_min_value, float std_max_value, void* stream);
 int stx_obs_normalize(const float* x, int64_t rows, int D, const float* mean, const float* std, float max_abs_value, void* out,
                       int out_bf16, void* stream);
+
+/* ---- Generic train-mode MLP (fp32 path): the autodiff of one network as two calls --------------------------------
+ * Replaces flax `apply` + `jax.grad` for networks outside the fused PPO kernels (ff_sac's actor and twin-Q networks,
+ * stoix/systems/sac/ff_sac.py:177-226): forward_train keeps the pre-activations (and LayerNorm statistics) of the torso
+ * in `workspace`; backward consumes d(loss)/d(output) and produces parameter gradients into `net_grad` (nullable; layout
+ * of StxMlp.params; grad = weight * g, added unless overwrite) and / or d(loss)/d(input) into `d_input` (nullable, dense
+ * M x sizes[0]) -- the latter is how the actor loss reaches the policy through Q(obs, action).  One workspace per
+ * forward whose backward is still pending. */
+size_t stx_mlp_train_workspace_bytes(const StxMlp* mlp, int64_t M);
+int stx_mlp_forward_train(const StxMlp* mlp, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int stx_mlp_backward(const StxMlp* mlp, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M, const float* d_out, void* workspace,
+                     size_t workspace_bytes, float grad_weight, float* net_grad, int overwrite, float* d_input, void* stream);
+
+/* ---- ff_sac building blocks (stoix/systems/sac/ff_sac.py:149-321) -------------------------------------------------
+ * tanh_normal_sample: NormalAffineTanhDistributionHead (stoix/networks/heads.py:44-65) on head_out[M][2A] = (loc | scale
+ *   pre-activation): action = shift + s tanh(loc + (softplus(raw) + min_scale) eps) written with leading dim ld_action
+ *   (e.g. straight into the action columns of the Q networks' concat(obs, action) input), log_prob of
+ *   AffineTanhTransformedDistribution (stoix/networks/distributions.py:19-79, clipped tails, epsilon 1e-3).  eps_in NULL:
+ *   eps ~ N(0,1) from Philox (seed, row, offset + *dev_counter); eps_out (nullable) keeps the noise for the backward.
+ * tanh_normal_backward: d(loss)/d(head_out) of loss = g_logp_scale * exp(*log_alpha) * sum_rows log_prob + sum g_action.action
+ *   under the reparameterisation (eps fixed): what jax.grad sees through `.sample(seed)` + `.log_prob` in _actor_loss_fn.
+ * sac_actor_seed: actor loss mean(alpha log_prob - min(q1, q2)) (:207-226): dq_k = -1/M on the arg-min network.
+ * sac_q_loss:     Q loss 0.5 mean((q_k - target)^2), target = r + (1-done) gamma (min next_q - alpha next_log_prob) (:177-205).
+ * sac_alpha_grad: alpha loss mean(alpha * (-log_prob - target_entropy)) and its gradient w.r.t. log_alpha (:157-175).
+ *   metrics[8] (accumulated with `weight`): actor_loss, entropy, q_loss, q_error, q1_pred, q2_pred, alpha_loss, alpha.
+ * polyak_update: optax.incremental_update: target = tau * online + (1 - tau) * target (:296-299).
+ * uniform_indices / gather_rows_f32 / gather_u8: the sampling half of the flashbax item buffer (uniform with replacement over
+ *   [0, *range)), rows gathered with a destination leading dimension. */
+int stx_tanh_normal_sample(const float* head_out, int64_t M, int A, const float* eps_in, uint64_t seed, uint64_t offset,
+                           const uint64_t* dev_counter, float minimum, float maximum, float min_scale, float* action, int64_t ld_action,
+                           float* log_prob, float* eps_out, void* stream);
+int stx_tanh_normal_backward(const float* head_out, const float* eps, int64_t M, int A, float minimum, float maximum, float min_scale,
+                             const float* log_alpha, float g_logp_scale, const float* g_action, int64_t ld_g_action, float* d_head_out,
+                             void* stream);
+int stx_sac_actor_seed(const float* q1, const float* q2, const float* log_prob, const float* log_alpha, int64_t M, float* dq1, float* dq2,
+                       float* metrics, float weight, void* stream);
+int stx_sac_q_loss(const float* q1, const float* q2, const float* next_q1, const float* next_q2, const float* next_log_prob,
+                   const float* reward, const uint8_t* done, const float* log_alpha, float gamma, int64_t M, float* dq1, float* dq2,
+                   float* metrics, float weight, void* stream);
+int stx_sac_alpha_grad(const float* log_prob, const float* log_alpha, float target_entropy, int64_t M, int autotune, float* grad,
+                       float grad_weight, int overwrite, float* metrics, float weight, void* stream);
+int stx_polyak_update(float* target, const float* online, int64_t n, float tau, void* stream);
+int stx_uniform_indices(int32_t* idx, int64_t M, uint64_t seed, uint64_t offset, const uint64_t* dev_counter, const int64_t* range,
+                        void* stream);
+int stx_gather_rows_f32(const float* src, const int32_t* idx, int64_t M, int C, float* dst, int64_t ld_dst, void* stream);
+int stx_gather_u8(const uint8_t* src, const int32_t* idx, int64_t M, uint8_t* dst, void* stream);
+
+/* Transition ring buffer -- the add / sample pair of flashbax's item buffer as ff_sac uses it (stoix/systems/sac/ff_sac.py:449-456:
+ * make_item_buffer(max_length, min_length, sample_batch_size, add_batches, add_sequences); add at :149-150, sample at :226-227).
+ * state: DEVICE int64[2] = {write position, number of valid items}: both calls are stream-ordered and CUDA-graph replayable.
+ *   add:    appends n rows (row-major, time-major order of the (T, E) batch), overwriting the oldest when full.
+ *   sample: M items uniform with replacement over the valid part (Philox (seed, row/4, offset + *dev_counter), the indices of
+ *           stx_uniform_indices; idx_in non-NULL overrides them) written as the network inputs of one SAC epoch with leading
+ *           dimension ld >= obs_dim + act_dim: xq_old = (obs | action), xq_new[:, :obs_dim] = obs, xq_next[:, :obs_dim] = next_obs
+ *           (the latter two nullable), plus reward[M], done[M], idx_out[M] (nullable). */
+typedef struct StxReplay {
+  float* obs;        /* [capacity][obs_dim] */
+  float* action;     /* [capacity][act_dim] */
+  float* reward;     /* [capacity] */
+  uint8_t* done;     /* [capacity] */
+  float* next_obs;   /* [capacity][obs_dim] */
+  int64_t* state;    /* device int64[2] */
+  int64_t capacity;
+  int32_t obs_dim;
+  int32_t act_dim;
+} StxReplay;
+int stx_replay_add(const StxReplay* rb, const float* obs, const float* action, const float* reward, const uint8_t* done,
+                   const float* next_obs, int64_t n, void* stream);
+int stx_replay_sample(const StxReplay* rb, int64_t M, uint64_t seed, uint64_t offset, const uint64_t* dev_counter, const int32_t* idx_in,
+                      float* xq_old, float* xq_new, float* xq_next, int64_t ld, float* reward, uint8_t* done, int32_t* idx_out,
+                      void* stream);
 
 /* Utility casts used by the bf16 path (obs / weight shadows). */
 int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

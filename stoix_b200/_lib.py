@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-STX_MAX_LAYERS = 4
+STX_MAX_LAYERS = 7
 STX_PREC_F32 = 0
 STX_PREC_BF16 = 1
 
@@ -81,6 +81,20 @@ class StxFusedAdam(C.Structure):
     ]
 
 
+class StxReplay(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p),
+        ("action", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("done", C.c_void_p),
+        ("next_obs", C.c_void_p),
+        ("state", C.c_void_p),
+        ("capacity", C.c_int64),
+        ("obs_dim", C.c_int32),
+        ("act_dim", C.c_int32),
+    ]
+
+
 class StxPpoBatch(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p),
@@ -130,6 +144,21 @@ _SIGNATURES = {
     "stx_tc_rollout_synth": (C.c_int, [C.POINTER(StxMlp)] + [_P] * 12 + [C.c_int, C.c_int64, C.c_uint64, C.c_uint64, _P, C.c_float, C.c_float,
                                         C.c_uint64, C.c_uint64, _P, _P]),
     "stx_cast_f32_to_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "stx_mlp_train_workspace_bytes": (C.c_size_t, [C.POINTER(StxMlp), C.c_int64]),
+    "stx_mlp_forward_train": (C.c_int, [C.POINTER(StxMlp), _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "stx_mlp_backward": (C.c_int, [C.POINTER(StxMlp), _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_size_t, C.c_float, _P, C.c_int, _P, _P]),
+    "stx_tanh_normal_sample": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_uint64, C.c_uint64, _P, C.c_float, C.c_float, C.c_float, _P, C.c_int64,
+                                         _P, _P, _P]),
+    "stx_tanh_normal_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, _P, C.c_float, _P, C.c_int64, _P, _P]),
+    "stx_sac_actor_seed": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_float, _P]),
+    "stx_sac_q_loss": (C.c_int, [_P] * 8 + [C.c_float, C.c_int64, _P, _P, _P, C.c_float, _P]),
+    "stx_sac_alpha_grad": (C.c_int, [_P, _P, C.c_float, C.c_int64, C.c_int, _P, C.c_float, C.c_int, _P, C.c_float, _P]),
+    "stx_polyak_update": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),
+    "stx_uniform_indices": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "stx_gather_rows_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int64, _P]),
+    "stx_gather_u8": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "stx_replay_add": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "stx_replay_sample": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "stx_running_stats_scratch_bytes": (C.c_size_t, [C.c_int]),
     "stx_running_stats_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, _P]),
     "stx_running_stats_finalize": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, _P]),

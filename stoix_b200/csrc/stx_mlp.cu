@@ -188,9 +188,10 @@ SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
   return w;
 }
 
-// backward of one network given d(head) in ws.dhead; accumulates grad_weight * grads into net_grad.
+// backward of one network given d(head) in ws.dhead; accumulates grad_weight * grads into net_grad (nullptr: parameter
+// gradients are not wanted); dx (nullable, mb x sizes[0], dense): receives d(loss)/d(input).
 int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t mb,
-                  const SimtPpoWs& ws, float grad_weight, float* net_grad, int overwrite, cudaStream_t st) {
+                  const SimtPpoWs& ws, float grad_weight, float* net_grad, int overwrite, cudaStream_t st, float* dx = nullptr) {
   int64_t woff[STX_MAX_LAYERS], boff[STX_MAX_LAYERS];
   layer_offsets(m, woff, boff);
   const int64_t np = stx_mlp_param_count(m);
@@ -213,8 +214,20 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
     g.rows_per_split = rows_per_split;
     g.part_stride = np, g.dbias_stride = np;
     dim3 grid((nout + simt::BN - 1) / simt::BN, (nin + simt::BM - 1) / simt::BM, ws.splits);
-    simt::gemm_kernel<simt::DW><<<grid, simt::kThreads, 0, st>>>(g);
-    STX_LAUNCH_OK();
+    if (net_grad != nullptr) {
+      simt::gemm_kernel<simt::DW><<<grid, simt::kThreads, 0, st>>>(g);
+      STX_LAUNCH_OK();
+    }
+    if (i == 0 && dx != nullptr) {  // d(input) = dY @ W_0^T (no activation in front of the first Dense)
+      simt::GemmArgs d{};
+      d.A = dY, d.lda = nout, d.a_act = -1, d.mask_act = -1;
+      d.B = m->params + woff[0];
+      d.C = dx;
+      d.M = mb, d.N = nin, d.K = nout;
+      dim3 gd((nin + simt::BN - 1) / simt::BN, (unsigned)((mb + simt::BM - 1) / simt::BM));
+      simt::gemm_kernel<simt::DX><<<gd, simt::kThreads, 0, st>>>(d);
+      STX_LAUNCH_OK();
+    }
     if (i > 0) {
       // d(U_{i-1}) from dY: through the Dense (dY @ W_i^T), the activation and, for LayerNorm torsos, the normalisation
       const bool ln = layer_has_ln(m, i - 1);
@@ -235,7 +248,8 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
             ws.dbuf[pp], ws.acts[i], ws.stats[i], gamma, gamma + nin, m->activation, mb, nin, ws.ln_rows, ws.ln_part);
         STX_LAUNCH_OK();
         // d(scale | bias) of layer i-1: fixed-order sum over the blocks, straight into the gradient arena
-        simt::reduce_partials_kernel<<<(unsigned)((2 * nin + 255) / 256), 256, 0, st>>>(ws.ln_part, ws.ln_blocks, 2 * (int64_t)nin, 2 * (int64_t)nin,
+        if (net_grad != nullptr)
+          simt::reduce_partials_kernel<<<(unsigned)((2 * nin + 255) / 256), 256, 0, st>>>(ws.ln_part, ws.ln_blocks, 2 * (int64_t)nin, 2 * (int64_t)nin,
                                                                                         grad_weight, net_grad + boff[i - 1], overwrite);
         STX_LAUNCH_OK();
       }
@@ -244,7 +258,7 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
     }
   }
   // fixed-order sum of the split-M partials: W_i and, for layers with a Dense bias, b_i (LayerNorm scale / bias were reduced above)
-  for (int i = 0; i < m->n_layers; ++i) {
+  for (int i = 0; i < m->n_layers && net_grad != nullptr; ++i) {
     const int64_t n = (int64_t)m->sizes[i] * m->sizes[i + 1] + (layer_has_ln(m, i) ? 0 : m->sizes[i + 1]);
     simt::reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.partials + woff[i], ws.splits, np, n, grad_weight,
                                                                               net_grad + woff[i], overwrite);
@@ -297,6 +311,36 @@ extern "C" int stx_mlp_forward(const StxMlp* m, const void* x, int64_t ldx, cons
     }
   }
   return simt_forward(m, reinterpret_cast<const float*>(x), ldx, row_idx, M, acts, stats, out, (cudaStream_t)stream);
+}
+
+// ---- generic train-mode MLP: forward keeping what the backward needs, backward to parameters and / or the input ----
+extern "C" size_t stx_mlp_train_workspace_bytes(const StxMlp* m, int64_t M) {
+  if (!m || M <= 0) return 0;
+  return carve(m, M, nullptr).bytes;
+}
+
+extern "C" int stx_mlp_forward_train(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M, float* out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_mlp(m, "stx_mlp_forward_train")) return rc;
+  STX_REQUIRE(x && out && workspace && M > 0, STX_E_ARG, "stx_mlp_forward_train: null pointer or M=%lld", (long long)M);
+  STX_REQUIRE(ldx >= m->sizes[0], STX_E_SHAPE, "stx_mlp_forward_train: ldx=%lld < in dim %d", (long long)ldx, m->sizes[0]);
+  STX_REQUIRE(workspace_bytes >= stx_mlp_train_workspace_bytes(m, M), STX_E_WORKSPACE, "stx_mlp_forward_train: workspace %zu < %zu",
+              workspace_bytes, stx_mlp_train_workspace_bytes(m, M));
+  SimtPpoWs ws = carve(m, M, reinterpret_cast<char*>(workspace));
+  return simt_forward(m, x, ldx, row_idx, M, ws.acts, ws.stats, out, (cudaStream_t)stream);
+}
+
+extern "C" int stx_mlp_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M, const float* d_out,
+                                void* workspace, size_t workspace_bytes, float grad_weight, float* net_grad, int overwrite, float* d_input,
+                                void* stream) {
+  if (int rc = check_mlp(m, "stx_mlp_backward")) return rc;
+  STX_REQUIRE(x && d_out && workspace && M > 0 && (net_grad || d_input), STX_E_ARG, "stx_mlp_backward: null pointer or nothing to compute");
+  STX_REQUIRE(workspace_bytes >= stx_mlp_train_workspace_bytes(m, M), STX_E_WORKSPACE, "stx_mlp_backward: workspace %zu < %zu", workspace_bytes,
+              stx_mlp_train_workspace_bytes(m, M));
+  SimtPpoWs ws = carve(m, M, reinterpret_cast<char*>(workspace));
+  cudaStream_t st = (cudaStream_t)stream;
+  STX_CUDA_OK(cudaMemcpyAsync(ws.dhead, d_out, sizeof(float) * (size_t)M * m->sizes[m->n_layers], cudaMemcpyDeviceToDevice, st));
+  return simt_backward(m, x, ldx, row_idx, M, ws, grad_weight, net_grad, overwrite, st, d_input);
 }
 
 extern "C" int stx_categorical(const float* logits, int64_t E, int A, int sample, uint64_t seed,

@@ -79,7 +79,11 @@ class _FeedForward:
         sl = spec.layer_slices()
         for i in range(spec.n_layers):
             scale = self.torso.kernel_init_scale if i < spec.n_layers - 1 else self.head.kernel_init_scale
-            host[sl[i][0]] = _orthogonal(gen, spec.sizes[i], spec.sizes[i + 1], scale).reshape(-1)
+            blocks = getattr(self.head, "kernel_blocks", None) if i == spec.n_layers - 1 else None
+            if blocks:  # several Dense heads side by side (NormalAffineTanhDistributionHead): independent orthogonal blocks
+                host[sl[i][0]] = torch.cat([_orthogonal(gen, spec.sizes[i], int(b), scale) for b in blocks], dim=1).reshape(-1)
+            else:
+                host[sl[i][0]] = _orthogonal(gen, spec.sizes[i], spec.sizes[i + 1], scale).reshape(-1)
             if spec.has_ln(i):
                 host[sl[i][1]] = 1.0  # LayerNorm scale = ones, bias = zeros (flax defaults)
         if flat is None:
@@ -87,8 +91,8 @@ class _FeedForward:
         flat[: spec.param_count].copy_(host)
         return build_param_tree(spec, flat, self.head_name)
 
-    def _forward(self, params: ParamTree, observation: torch.Tensor) -> torch.Tensor:
-        obs = self.input_layer(observation)
+    def _forward(self, params: ParamTree, observation: torch.Tensor, *extra) -> torch.Tensor:
+        obs = self.input_layer(observation, *extra)
         lead = obs.shape[:-1]
         x = obs.reshape(-1, obs.shape[-1])
         want = torch.bfloat16 if self.precision == ops.STX_PREC_BF16 else torch.float32
@@ -126,5 +130,41 @@ class FeedForwardCritic(_FeedForward):
 
     def apply(self, params: ParamTree, observation: torch.Tensor) -> torch.Tensor:
         return self._forward(params, observation).squeeze(-1)
+
+    __call__ = apply
+
+
+class FeedForwardQ(_FeedForward):
+    """One continuous Q network = CompositeNetwork([EmbeddingActionInput, MLPTorso, ScalarCriticHead]) of the reference
+    (stoix/networks/base.py:88-101 as built at stoix/systems/sac/ff_sac.py:357-366): apply(params, observation, action) -> (rows,)."""
+
+    head_name = "critic_head"
+
+    def __init__(self, critic_head, torso, input_layer=None):
+        from .inputs import EmbeddingActionInput
+
+        super().__init__(critic_head, torso, input_layer if input_layer is not None else EmbeddingActionInput())
+
+    def apply(self, params: ParamTree, observation: torch.Tensor, action: torch.Tensor) -> torch.Tensor:
+        return self._forward(params, observation, action).squeeze(-1)
+
+    __call__ = apply
+
+
+class MultiNetwork:
+    """stoix/networks/base.py:104-121: applies several networks to the same input and stacks the outputs on a new last axis;
+    parameters = a list with one ParamTree per member."""
+
+    def __init__(self, networks):
+        self.networks = list(networks)
+
+    def init(self, keys, x_and_a, flats=None):
+        from ..random import split
+
+        ks = split(keys, len(self.networks)) if not isinstance(keys, (list, tuple)) else list(keys)
+        return [n.init(k, x_and_a, flat=None if flats is None else flats[i]) for i, (n, k) in enumerate(zip(self.networks, ks))]
+
+    def apply(self, params, *network_input) -> torch.Tensor:
+        return torch.stack([n.apply(p, *network_input) for n, p in zip(self.networks, params)], dim=-1)
 
     __call__ = apply

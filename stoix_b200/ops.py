@@ -589,3 +589,171 @@ def obs_normalize(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out: O
                                              float(max_abs_value) if max_abs_value is not None else 0.0, _p(out),
                                              int(out.dtype == torch.bfloat16), _stream()), "stx_obs_normalize")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# generic train-mode MLP (fp32) + ff_sac building blocks (stoix/systems/sac/ff_sac.py:149-321)
+# ------------------------------------------------------------------------------------------------
+
+
+def mlp_train_workspace(spec: MlpSpec, M: int, device) -> torch.Tensor:
+    """Zero-filled workspace for mlp_forward_train / mlp_backward of a batch of M rows (one per pending backward)."""
+    m = _shape_only_struct(spec)
+    return torch.zeros(int(_lib.load().stx_mlp_train_workspace_bytes(C.byref(m), int(M))), dtype=torch.uint8, device=device)
+
+
+def mlp_forward_train(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, ws: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Forward that keeps the torso pre-activations (and LayerNorm statistics) in `ws` for mlp_backward.  x (M, >= in_dim)
+    float32, rows may be wider than the input dim (leading dimension x.stride(0))."""
+    dev = _need_cuda(params, ws, out)
+    if not x.is_cuda or x.dtype != torch.float32 or x.ndim != 2 or x.stride(1) != 1 or x.shape[1] < spec.sizes[0]:
+        raise StxError("mlp_forward_train: x must be a CUDA float32 matrix with unit column stride and >= in_dim columns")
+    M = int(x.shape[0])
+    if out is None:
+        out = torch.empty((M, spec.sizes[-1]), dtype=torch.float32, device=dev)
+    m = spec.c_struct(params)
+    _lib.check(_lib.load().stx_mlp_forward_train(C.byref(m), _p(x), x.stride(0), None, M, _p(out), _p(ws), ws.numel(), _stream()),
+               "stx_mlp_forward_train")
+    return out
+
+
+def mlp_backward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, d_out: torch.Tensor, ws: torch.Tensor,
+                 net_grad: Optional[torch.Tensor] = None, grad_weight: float = 1.0, overwrite: bool = True,
+                 d_input: Optional[torch.Tensor] = None) -> None:
+    """Backward of the forward that filled `ws`: parameter gradients into net_grad (layout of the parameter arena) and / or
+    d(loss)/d(input) into d_input (M, in_dim) dense."""
+    _need_cuda(params, d_out, ws, net_grad, d_input)
+    M = int(x.shape[0])
+    if d_out.dtype != torch.float32 or d_out.numel() != M * spec.sizes[-1]:
+        raise StxError("mlp_backward: d_out must be float32 (M, out_dim)")
+    if d_input is not None and (d_input.dtype != torch.float32 or d_input.numel() != M * spec.sizes[0]):
+        raise StxError("mlp_backward: d_input must be float32 (M, in_dim)")
+    m = spec.c_struct(params)
+    _lib.check(_lib.load().stx_mlp_backward(C.byref(m), _p(x), x.stride(0), None, M, _p(d_out), _p(ws), ws.numel(), float(grad_weight),
+                                            _p(net_grad), int(bool(overwrite)), _p(d_input), _stream()), "stx_mlp_backward")
+
+
+def tanh_normal_sample(head_out: torch.Tensor, minimum: float, maximum: float, min_scale: float = 1e-3, eps: Optional[torch.Tensor] = None,
+                       seed: int = 0, offset: int = 0, dev_counter: Optional[torch.Tensor] = None, action_out: Optional[torch.Tensor] = None,
+                       want_eps: bool = True):
+    """NormalAffineTanhDistributionHead sample + log_prob (heads.py:44-65, distributions.py:19-79) on head_out (M, 2A).
+    `action_out` may be a column block of a wider matrix (e.g. the Q networks' concat input).  Returns (action, log_prob, eps)."""
+    dev = _need_cuda(head_out, eps, dev_counter)
+    M, A2 = head_out.shape
+    A = A2 // 2
+    if action_out is None:
+        action_out = torch.empty(M, A, dtype=torch.float32, device=dev)
+    if action_out.stride(1) != 1 or action_out.shape != (M, A):
+        raise StxError("tanh_normal_sample: action_out must be (M, A) with unit column stride")
+    logp = torch.empty(M, dtype=torch.float32, device=dev)
+    eps_out = torch.empty(M, A, dtype=torch.float32, device=dev) if (want_eps and eps is None) else None
+    _lib.check(_lib.load().stx_tanh_normal_sample(_p(head_out), M, A, _p(eps), int(seed) & (2**64 - 1), int(offset), _p(dev_counter), float(minimum),
+                                                  float(maximum), float(min_scale), _p(action_out), action_out.stride(0), _p(logp), _p(eps_out),
+                                                  _stream()), "stx_tanh_normal_sample")
+    return action_out, logp, (eps if eps is not None else eps_out)
+
+
+def tanh_normal_backward(head_out: torch.Tensor, eps: torch.Tensor, minimum: float, maximum: float, log_alpha: Optional[torch.Tensor],
+                         g_logp_scale: float, g_action: Optional[torch.Tensor], min_scale: float = 1e-3,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d(loss)/d(head_out) for loss = g_logp_scale * exp(log_alpha) * sum log_prob + sum g_action * action (eps fixed)."""
+    dev = _need_cuda(head_out, eps, log_alpha)
+    M, A2 = head_out.shape
+    if out is None:
+        out = torch.empty(M, A2, dtype=torch.float32, device=dev)
+    if g_action is not None and (g_action.stride(1) != 1 or g_action.shape != (M, A2 // 2)):
+        raise StxError("tanh_normal_backward: g_action must be (M, A) with unit column stride")
+    _lib.check(_lib.load().stx_tanh_normal_backward(_p(head_out), _p(eps), M, A2 // 2, float(minimum), float(maximum), float(min_scale), _p(log_alpha),
+                                                    float(g_logp_scale), _p(g_action), g_action.stride(0) if g_action is not None else 0, _p(out),
+                                                    _stream()), "stx_tanh_normal_backward")
+    return out
+
+
+def sac_actor_seed(q1, q2, log_prob, log_alpha, dq1, dq2, metrics=None, weight: float = 1.0) -> None:
+    _need_cuda(q1, q2, log_prob, log_alpha, dq1, dq2, metrics)
+    _lib.check(_lib.load().stx_sac_actor_seed(_p(q1), _p(q2), _p(log_prob), _p(log_alpha), q1.numel(), _p(dq1), _p(dq2), _p(metrics), float(weight),
+                                              _stream()), "stx_sac_actor_seed")
+
+
+def sac_q_loss(q1, q2, next_q1, next_q2, next_log_prob, reward, done, log_alpha, gamma: float, dq1, dq2, metrics=None, weight: float = 1.0) -> None:
+    _need_cuda(q1, q2, next_q1, next_q2, next_log_prob, reward, done, log_alpha, dq1, dq2, metrics)
+    d8 = done.view(torch.uint8) if done.dtype == torch.bool else done
+    _lib.check(_lib.load().stx_sac_q_loss(_p(q1), _p(q2), _p(next_q1), _p(next_q2), _p(next_log_prob), _p(reward), _p(d8), _p(log_alpha), float(gamma),
+                                          q1.numel(), _p(dq1), _p(dq2), _p(metrics), float(weight), _stream()), "stx_sac_q_loss")
+
+
+def sac_alpha_grad(log_prob, log_alpha, target_entropy: float, autotune: bool, grad, grad_weight: float = 1.0, overwrite: bool = True,
+                   metrics=None, weight: float = 1.0) -> None:
+    _need_cuda(log_prob, log_alpha, grad, metrics)
+    _lib.check(_lib.load().stx_sac_alpha_grad(_p(log_prob), _p(log_alpha), float(target_entropy), log_prob.numel(), int(bool(autotune)), _p(grad),
+                                              float(grad_weight), int(bool(overwrite)), _p(metrics), float(weight), _stream()), "stx_sac_alpha_grad")
+
+
+def polyak_update(target: torch.Tensor, online: torch.Tensor, tau: float) -> None:
+    _need_cuda(target, online)
+    _lib.check(_lib.load().stx_polyak_update(_p(target), _p(online), target.numel(), float(tau), _stream()), "stx_polyak_update")
+
+
+def uniform_indices(M: int, range_dev: torch.Tensor, seed: int, offset: int = 0, dev_counter: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(range_dev, dev_counter, out)
+    if range_dev.dtype != torch.int64:
+        raise StxError("uniform_indices: range must be an int64 device scalar")
+    if out is None:
+        out = torch.empty(int(M), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().stx_uniform_indices(_p(out), int(M), int(seed) & (2**64 - 1), int(offset), _p(dev_counter), _p(range_dev), _stream()),
+               "stx_uniform_indices")
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[r, :C] = src[idx[r]] for float32 row-major src (N, C) / (N,), uint8 (N,); `out` may be a column block."""
+    _need_cuda(src, idx)
+    M = int(idx.numel())
+    if src.dtype == torch.uint8 or src.dtype == torch.bool:
+        s8, o8 = (src.view(torch.uint8) if src.dtype == torch.bool else src), (out.view(torch.uint8) if out.dtype == torch.bool else out)
+        _lib.check(_lib.load().stx_gather_u8(_p(s8), _p(idx), M, _p(o8), _stream()), "stx_gather_u8")
+        return out
+    Cn = 1 if src.ndim == 1 else int(src.shape[1])
+    ld = 1 if out.ndim == 1 else out.stride(0)
+    _lib.check(_lib.load().stx_gather_rows_f32(_p(src), _p(idx), M, Cn, _p(out), int(ld), _stream()), "stx_gather_rows_f32")
+    return out
+
+
+class ReplayRing:
+    """Device storage + StxReplay descriptor of the transition ring buffer (stx_replay_add / stx_replay_sample)."""
+
+    def __init__(self, capacity: int, obs_dim: int, act_dim: int, device):
+        self.capacity, self.obs_dim, self.act_dim = int(capacity), int(obs_dim), int(act_dim)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
+        self.obs, self.next_obs = z(self.capacity, self.obs_dim), z(self.capacity, self.obs_dim)
+        self.action, self.reward, self.done = z(self.capacity, self.act_dim), z(self.capacity), z(self.capacity, dt=torch.uint8)
+        self.state = z(2, dt=torch.int64)   # {write position, valid items}
+        self.c = _lib.StxReplay(_p(self.obs), _p(self.action), _p(self.reward), _p(self.done), _p(self.next_obs), _p(self.state), self.capacity,
+                                self.obs_dim, self.act_dim)
+
+
+def replay_add(rb: ReplayRing, obs, action, reward, done, next_obs) -> None:
+    """Append the rows of a (T, E, ...) / (n, ...) batch of transitions (contiguous fp32; done uint8 / bool)."""
+    _need_cuda(obs, action, reward, done, next_obs)
+    n = int(reward.numel())
+    for t, cols, name in ((obs, rb.obs_dim, "obs"), (next_obs, rb.obs_dim, "next_obs"), (action, rb.act_dim, "action"), (reward, 1, "reward")):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n * cols:
+            raise StxError(f"replay_add: {name} must be contiguous float32 with {n} x {cols} elements")
+    d8 = done.view(torch.uint8) if done.dtype == torch.bool else done
+    if d8.dtype != torch.uint8 or not d8.is_contiguous() or d8.numel() != n:
+        raise StxError("replay_add: done must be contiguous uint8 / bool")
+    _lib.check(_lib.load().stx_replay_add(C.byref(rb.c), _p(obs), _p(action), _p(reward), _p(d8), _p(next_obs), n, _stream()), "stx_replay_add")
+
+
+def replay_sample(rb: ReplayRing, M: int, seed: int, xq_old: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, xq_new=None, xq_next=None,
+                  offset: int = 0, dev_counter: Optional[torch.Tensor] = None, idx_in: Optional[torch.Tensor] = None,
+                  idx_out: Optional[torch.Tensor] = None) -> None:
+    """One launch: draw M indices (or take idx_in) and write (obs | action), (obs | .), (next_obs | .), reward, done."""
+    _need_cuda(xq_old, xq_new, xq_next, reward, done, dev_counter, idx_in, idx_out)
+    ld = xq_old.stride(0)
+    for t in (xq_old, xq_new, xq_next):
+        if t is not None and (t.dtype != torch.float32 or t.shape[0] != M or t.stride(0) != ld or t.stride(1) != 1):
+            raise StxError("replay_sample: xq_* must be float32 (M, >= obs_dim + act_dim) with one common leading dimension")
+    _lib.check(_lib.load().stx_replay_sample(C.byref(rb.c), int(M), int(seed) & (2**64 - 1), int(offset), _p(dev_counter), _p(idx_in), _p(xq_old),
+                                             _p(xq_new), _p(xq_next), int(ld), _p(reward), _p(done), _p(idx_out), _stream()), "stx_replay_sample")

@@ -26,6 +26,12 @@ def make(config) -> Tuple[Environment, Environment]:
         env = SyntheticBoxEnv(seed=seed + 7919 * rank, device=device, obs_dtype=obs_dtype, **kw)
         eval_env = SyntheticBoxEnv(seed=seed + 104729 + 7919 * rank, device=device, obs_dtype=obs_dtype, **kw)
         return env, eval_env
+    if name == "synthetic_continuous":
+        from ..envs.synthetic_continuous import SyntheticContinuousEnv
+
+        kw = dict(config.env.kwargs)
+        return (SyntheticContinuousEnv(seed=seed + 7919 * rank, device=device, **kw),
+                SyntheticContinuousEnv(seed=seed + 104729 + 7919 * rank, device=device, **kw))
     if name == "gymnax":
         scenario = config.env.scenario.name
         if scenario != "CartPole-v1":

@@ -40,11 +40,12 @@ def test_binding_matches_header():
 def test_struct_layouts_match_c():
     from stoix_b200 import _lib
 
-    assert ctypes.sizeof(_lib.StxMlp) == 4 + 5 * 4 + 8 + 8 + 4 + 4
+    assert ctypes.sizeof(_lib.StxMlp) == (4 + 8 * 4 + 4) + 8 + 8 + 4 + 4  # n_layers, sizes[8], pad to 8, two pointers, two ints
     assert ctypes.sizeof(_lib.StxAdamSeg) == 24
     assert ctypes.sizeof(_lib.StxAdamHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoHyper) == 32
     assert ctypes.sizeof(_lib.StxPpoBatch) == 72
+    assert ctypes.sizeof(_lib.StxReplay) == 6 * 8 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.StxFusedAdam) == 5 * 8 + 8 + 32 + 3 * 8
 
 
