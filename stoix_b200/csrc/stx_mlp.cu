@@ -52,43 +52,40 @@ void layer_offsets(const StxMlp* m, int64_t* woff, int64_t* boff) {
   }
 }
 
-// operand transform of the GEMM that consumes the output of torso layer `prev` (see stx_simt_gemm.cuh)
-void set_operand_transform(simt::GemmArgs& g, const StxMlp* m, int prev, const int64_t* boff, float* const* stats) {
-  g.a_act = m->activation;
-  if (layer_has_ln(m, prev)) {
-    g.a_stats = stats[prev + 1];
-    g.a_gamma = m->params + boff[prev];
-    g.a_beta = m->params + boff[prev] + m->sizes[prev + 1];
-  }
-}
-
-// Forward through all layers.  acts[i] (i=1..n-1) receive the PRE-activation Dense outputs U_i (M x sizes[i]), stats[i]
-// (LayerNorm torsos) their per-row (mean, rstd); the head output goes to `out`.  x may be gathered through row_idx.
+// Forward through all layers.  For the torso layers i = 1..n-1: acts[i] (nullable: inference) receive the PRE-activation Dense
+// outputs U_i (M x sizes[i]), hacts[i] the layer outputs H_i = f(U_i) / f(LN(U_i)) the next layer multiplies, stats[i] (nullable)
+// the LayerNorm (mean, rstd); the head output goes to `out`.  x may be gathered through row_idx.
 int simt_forward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M,
-                 float* const* acts, float* const* stats, float* out, cudaStream_t st) {
+                 float* const* acts, float* const* hacts, float* const* stats, float* out, cudaStream_t st) {
   int64_t woff[STX_MAX_LAYERS], boff[STX_MAX_LAYERS];
   layer_offsets(m, woff, boff);
   const float* in = x;
   int64_t ld = ldx;
   const int32_t* ridx = row_idx;
   for (int i = 0; i < m->n_layers; ++i) {
-    const bool last = (i == m->n_layers - 1);
+    const bool last = (i == m->n_layers - 1), ln = layer_has_ln(m, i);
     simt::GemmArgs g{};
     g.A = in, g.lda = ld, g.rowidx = ridx;
-    g.a_act = -1, g.mask_act = -1;
-    if (i > 0) set_operand_transform(g, m, i - 1, boff, stats);  // MLPTorso activate_final=True: the head sees f(.) too
+    g.mask_act = -1;
     g.B = m->params + woff[i];
-    g.bias = layer_has_ln(m, i) ? nullptr : m->params + boff[i];  // torso.py:26: use_bias = not use_layer_norm
-    g.C = last ? out : acts[i + 1];
+    g.bias = ln ? nullptr : m->params + boff[i];  // torso.py:26: use_bias = not use_layer_norm
     g.M = M, g.N = m->sizes[i + 1], g.K = m->sizes[i];
-    dim3 grid((g.N + simt::BN - 1) / simt::BN, (unsigned)((M + simt::BM - 1) / simt::BM));
-    simt::gemm_kernel<simt::FWD><<<grid, simt::kThreads, 0, st>>>(g);
-    STX_LAUNCH_OK();
-    if (layer_has_ln(m, i)) {
-      simt::ln_stats_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(acts[i + 1], M, g.N, stats[i + 1]);
+    if (last) {
+      g.C = out;
+    } else if (ln) {   // U now; H = f(LN(U)) by ln_apply_kernel (inference: in place on the H buffer)
+      g.C = acts[i + 1] ? acts[i + 1] : hacts[i + 1];
+    } else {           // MLPTorso activate_final=True: the head sees f(.) too
+      g.C = acts[i + 1];
+      g.C_act = hacts[i + 1], g.c_act = m->activation;
+    }
+    STX_CUDA_OK(simt::launch_gemm<simt::FWD>(g, 1, st));
+    if (ln) {
+      const float* gamma = m->params + boff[i];
+      simt::ln_apply_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(g.C, M, g.N, gamma, gamma + g.N, m->activation, stats ? stats[i + 1] : nullptr,
+                                                                     hacts[i + 1]);
       STX_LAUNCH_OK();
     }
-    in = g.C, ld = g.N, ridx = nullptr;
+    in = last ? out : hacts[i + 1], ld = g.N, ridx = nullptr;
   }
   return STX_OK;
 }
@@ -140,7 +137,8 @@ __global__ void categorical_kernel(const float* __restrict__ logits, int64_t E, 
 
 // ---- fp32 PPO minibatch: workspace carving -------------------------------------------------
 struct SimtPpoWs {
-  float* acts[STX_MAX_LAYERS + 1];  // pre-activation Dense outputs of the torso layers, index 1..n-1
+  float* acts[STX_MAX_LAYERS + 1];  // pre-activation Dense outputs U_i of the torso layers, index 1..n-1
+  float* hacts[STX_MAX_LAYERS + 1]; // layer outputs H_i = f(U_i) / f(LN(U_i)): the operand of the next layer's GEMMs
   float* stats[STX_MAX_LAYERS + 1]; // LayerNorm torsos: per-row (mean, rstd) of acts[i]
   float* ln_part;                   // LayerNorm backward: [blocks][2 * width] column-sum partials
   int ln_blocks, ln_rows;
@@ -173,8 +171,11 @@ SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
   w.counter = reinterpret_cast<unsigned int*>(take(256));
   const int mw = max_width(m);
   for (int i = 1; i < m->n_layers; ++i) w.acts[i] = reinterpret_cast<float*>(take((size_t)mb * m->sizes[i] * 4));
+  for (int i = 1; i < m->n_layers; ++i) w.hacts[i] = reinterpret_cast<float*>(take((size_t)mb * m->sizes[i] * 4));
   for (int i = 1; i < m->n_layers; ++i) w.stats[i] = m->use_layer_norm ? reinterpret_cast<float*>(take((size_t)mb * 2 * 4)) : nullptr;
-  w.ln_rows = 128;  // rows per block of ln_backward_kernel
+  // rows per block of ln_backward_kernel: about two blocks per SM, a whole number of rows per warp
+  w.ln_rows = (int)(((mb + 295) / 296 + simt::kLnWarps - 1) / simt::kLnWarps * simt::kLnWarps);
+  if (w.ln_rows > 128) w.ln_rows = 128;
   w.ln_blocks = (int)((mb + w.ln_rows - 1) / w.ln_rows);
   w.ln_part = m->use_layer_norm ? reinterpret_cast<float*>(take((size_t)w.ln_blocks * 2 * mw * 4)) : nullptr;
   w.head = reinterpret_cast<float*>(take((size_t)mb * m->sizes[m->n_layers] * 4));
@@ -200,48 +201,38 @@ int simt_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* r
   int pp = 0;
   for (int i = m->n_layers - 1; i >= 0; --i) {
     const int nin = m->sizes[i], nout = m->sizes[i + 1];
-    // dW_i, db_i partials: input of layer i is x (gathered) for i==0 else f(acts[i]) / f(LN(acts[i])) rebuilt on load
+    // dW_i, db_i partials: input of layer i is x (gathered) for i == 0, else the stored layer output H_i
     simt::GemmArgs g{};
-    g.A = (i == 0) ? x : ws.acts[i];
+    g.A = (i == 0) ? x : ws.hacts[i];
     g.lda = (i == 0) ? ldx : nin;
     g.rowidx = (i == 0) ? row_idx : nullptr;
-    g.a_act = -1, g.mask_act = -1;
-    if (i > 0) set_operand_transform(g, m, i - 1, boff, ws.stats);
+    g.mask_act = -1;
     g.B = dY;
     g.C = ws.partials + woff[i];
     g.dbias = layer_has_ln(m, i) ? nullptr : ws.partials + boff[i];  // LayerNorm layers: Dense has no bias (scale / bias below)
     g.M = mb, g.N = nout, g.K = nin;
     g.rows_per_split = rows_per_split;
     g.part_stride = np, g.dbias_stride = np;
-    dim3 grid((nout + simt::BN - 1) / simt::BN, (nin + simt::BM - 1) / simt::BM, ws.splits);
-    if (net_grad != nullptr) {
-      simt::gemm_kernel<simt::DW><<<grid, simt::kThreads, 0, st>>>(g);
-      STX_LAUNCH_OK();
-    }
+    if (net_grad != nullptr) STX_CUDA_OK(simt::launch_gemm<simt::DW>(g, ws.splits, st));
     if (i == 0 && dx != nullptr) {  // d(input) = dY @ W_0^T (no activation in front of the first Dense)
       simt::GemmArgs d{};
-      d.A = dY, d.lda = nout, d.a_act = -1, d.mask_act = -1;
+      d.A = dY, d.lda = nout, d.mask_act = -1;
       d.B = m->params + woff[0];
       d.C = dx;
       d.M = mb, d.N = nin, d.K = nout;
-      dim3 gd((nin + simt::BN - 1) / simt::BN, (unsigned)((mb + simt::BM - 1) / simt::BM));
-      simt::gemm_kernel<simt::DX><<<gd, simt::kThreads, 0, st>>>(d);
-      STX_LAUNCH_OK();
+      STX_CUDA_OK(simt::launch_gemm<simt::DX>(d, 1, st));
     }
     if (i > 0) {
       // d(U_{i-1}) from dY: through the Dense (dY @ W_i^T), the activation and, for LayerNorm torsos, the normalisation
       const bool ln = layer_has_ln(m, i - 1);
       simt::GemmArgs d{};
       d.A = dY, d.lda = nout;
-      d.a_act = -1;
       d.B = m->params + woff[i];
       d.C = ws.dbuf[pp];
       d.mask = ln ? nullptr : ws.acts[i];
       d.mask_act = ln ? -1 : m->activation;
       d.M = mb, d.N = nin, d.K = nout;
-      dim3 gd((nin + simt::BN - 1) / simt::BN, (unsigned)((mb + simt::BM - 1) / simt::BM));
-      simt::gemm_kernel<simt::DX><<<gd, simt::kThreads, 0, st>>>(d);
-      STX_LAUNCH_OK();
+      STX_CUDA_OK(simt::launch_gemm<simt::DX>(d, 1, st));
       if (ln) {
         const float* gamma = m->params + boff[i - 1];
         simt::ln_backward_kernel<<<ws.ln_blocks, 32 * simt::kLnWarps, sizeof(float) * simt::kLnWarps * 2 * nin, st>>>(
@@ -284,7 +275,7 @@ extern "C" size_t stx_mlp_forward_workspace_bytes(const StxMlp* m, int64_t M, in
   if (!m || M <= 0) return 0;
   if (precision == STX_PREC_BF16) return tc_mlp_forward_workspace_bytes(m, M);
   size_t o = 0;
-  for (int i = 1; i < m->n_layers; ++i) o += align_up((size_t)M * m->sizes[i] * 4) + (m->use_layer_norm ? align_up((size_t)M * 8) : 0);
+  for (int i = 1; i < m->n_layers; ++i) o += align_up((size_t)M * m->sizes[i] * 4);
   return o > 0 ? o : 256;
 }
 
@@ -299,18 +290,14 @@ extern "C" int stx_mlp_forward(const StxMlp* m, const void* x, int64_t ldx, cons
   if (precision == STX_PREC_BF16)
     return tc_mlp_forward(m, x, ldx, row_idx, M, out, workspace, workspace_bytes, (cudaStream_t)stream);
   STX_REQUIRE(precision == STX_PREC_F32, STX_E_UNSUPPORTED, "stx_mlp_forward: precision=%d", precision);
-  float* acts[STX_MAX_LAYERS + 1] = {nullptr};
-  float* stats[STX_MAX_LAYERS + 1] = {nullptr};
+  float* acts[STX_MAX_LAYERS + 1] = {nullptr};   // inference: pre-activations are not kept
+  float* hacts[STX_MAX_LAYERS + 1] = {nullptr};
   char* p = reinterpret_cast<char*>(workspace);
   for (int i = 1; i < m->n_layers; ++i) {
-    acts[i] = reinterpret_cast<float*>(p);
+    hacts[i] = reinterpret_cast<float*>(p);
     p += align_up((size_t)M * m->sizes[i] * 4);
-    if (m->use_layer_norm) {
-      stats[i] = reinterpret_cast<float*>(p);
-      p += align_up((size_t)M * 8);
-    }
   }
-  return simt_forward(m, reinterpret_cast<const float*>(x), ldx, row_idx, M, acts, stats, out, (cudaStream_t)stream);
+  return simt_forward(m, reinterpret_cast<const float*>(x), ldx, row_idx, M, acts, hacts, nullptr, out, (cudaStream_t)stream);
 }
 
 // ---- generic train-mode MLP: forward keeping what the backward needs, backward to parameters and / or the input ----
@@ -327,7 +314,7 @@ extern "C" int stx_mlp_forward_train(const StxMlp* m, const float* x, int64_t ld
   STX_REQUIRE(workspace_bytes >= stx_mlp_train_workspace_bytes(m, M), STX_E_WORKSPACE, "stx_mlp_forward_train: workspace %zu < %zu",
               workspace_bytes, stx_mlp_train_workspace_bytes(m, M));
   SimtPpoWs ws = carve(m, M, reinterpret_cast<char*>(workspace));
-  return simt_forward(m, x, ldx, row_idx, M, ws.acts, ws.stats, out, (cudaStream_t)stream);
+  return simt_forward(m, x, ldx, row_idx, M, ws.acts, ws.hacts, ws.stats, out, (cudaStream_t)stream);
 }
 
 extern "C" int stx_mlp_backward(const StxMlp* m, const float* x, int64_t ldx, const int32_t* row_idx, int64_t M, const float* d_out,
@@ -431,7 +418,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
   // ---- actor: forward, loss, backward (ff_ppo.py:191-213, 238-241) ----
   {
     SimtPpoWs ws = carve(actor, mb, reinterpret_cast<char*>(workspace));
-    if (int rc = simt_forward(actor, x, D, idx, mb, ws.acts, ws.stats, ws.head, st)) return rc;
+    if (int rc = simt_forward(actor, x, D, idx, mb, ws.acts, ws.hacts, ws.stats, ws.head, st)) return rc;
     LossArgs g{};
     g.logits = ws.head, g.value = nullptr, g.idx = idx, g.row0 = mb_off;
     g.action = b->action, g.logp_old = b->log_prob, g.v_old = b->value, g.adv = b->advantages, g.tgt = b->targets;
@@ -445,7 +432,7 @@ extern "C" int stx_ppo_minibatch_grads(const StxMlp* actor, const StxMlp* critic
   // ---- critic: forward, loss, backward (ff_ppo.py:215-235, 244-247) ----
   {
     SimtPpoWs ws = carve(critic, mb, reinterpret_cast<char*>(workspace));
-    if (int rc = simt_forward(critic, x, D, idx, mb, ws.acts, ws.stats, ws.head, st)) return rc;
+    if (int rc = simt_forward(critic, x, D, idx, mb, ws.acts, ws.hacts, ws.stats, ws.head, st)) return rc;
     LossArgs g{};
     g.logits = nullptr, g.value = ws.head, g.value_ld = 1, g.idx = idx, g.row0 = mb_off;
     g.action = b->action, g.logp_old = b->log_prob, g.v_old = b->value, g.adv = b->advantages, g.tgt = b->targets;

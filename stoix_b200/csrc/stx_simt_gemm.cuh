@@ -3,14 +3,14 @@
 // The reference is fp32 everywhere (SURVEY.md "facts"), so this path keeps every product and
 // accumulation in fp32 and is what the tight-tolerance parity tests run.  The bf16 tcgen05 path
 // (stx_tc_*.cu) is the throughput path.  Three flavours of one 64x64x16 register-tiled kernel:
-//   FWD : U[m,n]  = sum_k A'[row(m),k] * W[k,n] (+ b[n])                    nn.Dense, torso.py:26
+//   FWD : U[m,n]  = sum_k H_prev[row(m),k] * W[k,n] (+ b[n])                nn.Dense, torso.py:26
 //   DX  : dU_prev[m,k] = (sum_n dY[m,n] * W[k,n]) * f'(U_prev[m,k])         backward through the activation (no-LayerNorm torso)
-//   DW  : dWp[z][k,n] = sum_{m in slice z} A'[row(m),k] * dY[m,n],  dbp[z][n] = sum dY[m,n]
-// Hidden layers are stored PRE-activation (U = the Dense output): the operand A' of the next GEMM is rebuilt on load,
-//   A' = f(U)                               MLPTorso(activation=f)                       torso.py:31-32, networks/utils.py:9-24
-//   A' = f(LN(U) * scale + bias)            MLPTorso(use_layer_norm=True): Dense without bias, nn.LayerNorm (eps 1e-6) torso.py:26-30
-// which keeps one code path for every activation (f' is evaluated from U; for relu f(U) > 0 <=> U > 0, so the relu
-// numbers are those of the former post-activation storage) and lets LayerNorm use per-row statistics computed once.
+//   DW  : dWp[z][k,n] = sum_{m in slice z} H_prev[row(m),k] * dY[m,n],  dbp[z][n] = sum dY[m,n]
+// Hidden layers keep BOTH the pre-activation U (the Dense output: f' and the LayerNorm backward are evaluated from it) and the
+// layer output H the next GEMMs multiply, computed ONCE per element:
+//   H = f(U)                               MLPTorso(activation=f): FWD epilogue               torso.py:31-32, networks/utils.py:9-24
+//   H = f(LN(U) * scale + bias)            MLPTorso(use_layer_norm=True): ln_apply_kernel (Dense without bias, eps 1e-6) torso.py:26-30
+// (rebuilding H on every operand load cost 8 redundant exp per element and made the small GEMMs transcendental-bound).
 // All shapes are bounds-checked (D=4, A=2 of CartPole work).  Split-M partials of DW are reduced in
 // a fixed order by reduce_partials_kernel -> run-to-run deterministic gradients.
 #pragma once
@@ -66,30 +66,40 @@ __device__ __forceinline__ float act_grad(int kind, float z) {
 }
 
 struct GemmArgs {
-  // FWD: A=X (M x K, lda, optional row gather), B=W (K x N), C=Y (M x N)
-  // DX : A=dY (M x Nr, lda=Nr), B=W (Kout x Nr) used transposed, C=dX (M x Kout), mask=H (M x Kout)
-  // DW : A=X (rows x Kout, gathered), B=dY (rows x N), C=partials [z][Kout x N]
+  // FWD: A=H_prev (M x K, lda, optional row gather), B=W (K x N), C=U (M x N, nullable), C_act=f(U) (nullable)
+  // DX : A=dY (M x Nr, lda=Nr), B=W (Kout x Nr) used transposed, C=dX (M x Kout), mask=U (M x Kout)
+  // DW : A=H_prev (rows x Kout, gathered), B=dY (rows x N), C=partials [z][Kout x N]
   const float* A;
   const float* B;
   float* C;
+  float* C_act;          // FWD: post-activation copy f(U) for the next layer's GEMMs (no-LayerNorm torsos); nullable
+  int c_act;             // FWD: the activation of C_act
   const float* bias;     // FWD
-  const float* mask;     // DX: post-activation tensor of the producing layer (ld = ldc)
+  const float* mask;     // DX: pre-activation tensor of the producing layer (ld = N)
   const int32_t* rowidx; // FWD/DW: gather index for A rows (nullable)
   float* dbias;          // DW: partial db [z][N]
   int64_t M;             // FWD/DX: output rows.  DW: total sample rows (reduction length)
   int N;                 // output columns
   int K;                 // FWD: reduction (in dim).  DX: reduction (= layer out dim).  DW: output rows (in dim)
   int64_t lda;
-  // operand transform on load (FWD / DW): A' = f(A) or f(LN(A) * gamma + beta); a_act < 0: A is used as it is (network input)
-  int a_act;
-  const float* a_stats;  // [rows][2] (mean, rstd) of A's rows, LayerNorm torsos only
-  const float* a_gamma;  // [K] / [features]
-  const float* a_beta;
   int mask_act;          // DX epilogue: activation whose derivative (from `mask` = U) multiplies the result; < 0: none
   int64_t rows_per_split;  // DW
   int64_t part_stride;   // DW: floats between split partials of this layer
   int64_t dbias_stride;  // DW
 };
+
+// Epilogue shared by both tilings: one output element.
+template <int MODE>
+__device__ __forceinline__ void store_out(const GemmArgs& g, int64_t m, int n, float acc) {
+  if (MODE == FWD) {
+    const float u = acc + (g.bias ? __ldg(g.bias + n) : 0.f);
+    if (g.C) g.C[m * g.N + n] = u;                                   // pre-activation (backward: f' and LayerNorm need it)
+    if (g.C_act) g.C_act[m * g.N + n] = act_fwd(g.c_act, u);         // what the next GEMM multiplies
+  } else {
+    const float d = (g.mask && g.mask_act >= 0) ? act_grad(g.mask_act, __ldg(g.mask + m * g.N + n)) : 1.f;
+    g.C[m * g.N + n] = acc * d;
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
@@ -108,80 +118,65 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
 
   // reduction range
   int64_t r_begin = 0, r_end;
-  if (MODE == FWD) r_end = g.K;
-  else if (MODE == DX) r_end = g.K;
-  else {
+  if (MODE == DW) {
     r_begin = (int64_t)blockIdx.z * g.rows_per_split;
     r_end = r_begin + g.rows_per_split;
     if (r_end > g.M) r_end = g.M;
+  } else {
+    r_end = g.K;
   }
   const int out_rows = (MODE == DW) ? g.K : 0;  // DW: output rows = in-dim
 
   for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
-    // ---- load A tile into As[kk][m] ----
-    if (MODE == FWD) {
-      // X[row(m), r0+kk]: kk fastest in memory
-      for (int i = tid; i < BM * BK; i += kThreads) {
-        const int kk = i % BK, mm = i / BK;
+    // All global loads of the step go to registers first (read-only path), then the shared stores: a load -> store -> load
+    // loop would serialise on the memory latency (the compiler cannot prove a generic pointer does not alias shared memory).
+    constexpr int LA = BM * BK / kThreads, LB = BN * BK / kThreads;  // 4, 4
+    float va[LA], vb[LB];
+    if (MODE == FWD || MODE == DX) {  // A[row(m)][r0 + kk]: kk fastest in memory -> As[kk][m]
+#pragma unroll
+      for (int u = 0; u < LA; ++u) {
+        const int i = tid + u * kThreads, kk = i % BK, mm = i / BK;
         const int64_t m = m0 + mm, k = r0 + kk;
-        float v = 0.f;
-        if (m < g.M && k < r_end) {
-          const int64_t row = g.rowidx ? (int64_t)g.rowidx[m] : m;
-          v = g.A[row * g.lda + k];
-          if (g.a_act >= 0) {
-            if (g.a_stats) v = (v - g.a_stats[2 * row]) * g.a_stats[2 * row + 1] * g.a_gamma[k] + g.a_beta[k];
-            v = act_fwd(g.a_act, v);
-          }
-        }
-        As[kk][mm] = v;
+        const bool ok = m < g.M && k < r_end;
+        const int64_t row = ok ? ((MODE == FWD && g.rowidx) ? (int64_t)__ldg(g.rowidx + m) : m) : 0;
+        va[u] = ok ? __ldg(g.A + row * g.lda + k) : 0.f;
       }
-    } else if (MODE == DX) {
-      // dY[m, r0+kk]
-      for (int i = tid; i < BM * BK; i += kThreads) {
-        const int kk = i % BK, mm = i / BK;
-        const int64_t m = m0 + mm, k = r0 + kk;
-        As[kk][mm] = (m < g.M && k < r_end) ? g.A[m * g.lda + k] : 0.f;
-      }
-    } else {
-      // DW: A(i, r) = X[row(r), i]; i (feature) fastest in memory. As[kk=r][mm=i]
-      for (int i = tid; i < BM * BK; i += kThreads) {
-        const int mm = i % BM, kk = i / BM;
+    } else {  // DW: A(f, r) = H[row(r)][f]; f (feature) fastest in memory. As[kk = r][mm = f]
+#pragma unroll
+      for (int u = 0; u < LA; ++u) {
+        const int i = tid + u * kThreads, mm = i % BM, kk = i / BM;
         const int64_t r = r0 + kk, f = m0 + mm;
-        float v = 0.f;
-        if (r < r_end && f < out_rows) {
-          const int64_t row = g.rowidx ? (int64_t)g.rowidx[r] : r;
-          v = g.A[row * g.lda + f];
-          if (g.a_act >= 0) {
-            if (g.a_stats) v = (v - g.a_stats[2 * row]) * g.a_stats[2 * row + 1] * g.a_gamma[f] + g.a_beta[f];
-            v = act_fwd(g.a_act, v);
-          }
-        }
-        As[kk][mm] = v;
+        const bool ok = r < r_end && f < out_rows;
+        const int64_t row = ok ? (g.rowidx ? (int64_t)__ldg(g.rowidx + r) : r) : 0;
+        va[u] = ok ? __ldg(g.A + row * g.lda + f) : 0.f;
       }
     }
-    // ---- load B tile into Bs[kk][n] ----
-    if (MODE == FWD) {
-      for (int i = tid; i < BN * BK; i += kThreads) {
-        const int nn = i % BN, kk = i / BN;
-        const int64_t k = r0 + kk;
-        const int n = n0 + nn;
-        Bs[kk][nn] = (k < r_end && n < g.N) ? g.B[k * g.N + n] : 0.f;
-      }
-    } else if (MODE == DX) {
-      // B(kk, j) = W[j, r0+kk], W is (Kout x Nr) row-major; output col j = n0+nn; reduction fastest
-      for (int i = tid; i < BN * BK; i += kThreads) {
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int i = tid + u * kThreads;
+      if (MODE == DX) {  // B(kk, j) = W[j][r0 + kk], W (Kout x Nr) row-major; reduction fastest in memory
         const int kk = i % BK, nn = i / BK;
         const int64_t k = r0 + kk;
         const int j = n0 + nn;
-        Bs[kk][nn] = (k < r_end && j < g.N) ? g.B[(int64_t)j * g.K + k] : 0.f;
-      }
-    } else {
-      for (int i = tid; i < BN * BK; i += kThreads) {
+        vb[u] = (k < r_end && j < g.N) ? __ldg(g.B + (int64_t)j * g.K + k) : 0.f;
+      } else {           // FWD: W[k][n]; DW: dY[r][n]
         const int nn = i % BN, kk = i / BN;
-        const int64_t r = r0 + kk;
+        const int64_t k = r0 + kk;
         const int n = n0 + nn;
-        Bs[kk][nn] = (r < r_end && n < g.N) ? g.B[r * g.N + n] : 0.f;
+        vb[u] = (k < r_end && n < g.N) ? __ldg(g.B + k * g.N + n) : 0.f;
       }
+    }
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int i = tid + u * kThreads;
+      if (MODE == DW) As[i / BM][i % BM] = va[u];
+      else As[i % BK][i / BK] = va[u];
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int i = tid + u * kThreads;
+      if (MODE == DX) Bs[i % BK][i / BK] = vb[u];
+      else Bs[i / BN][i % BN] = vb[u];
     }
     __syncthreads();
 #pragma unroll
@@ -204,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
   }
 
   // ---- epilogue ----
-  if (MODE == FWD) {
+  if (MODE != DW) {
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
       const int64_t m = m0 + ty * TM + i;
@@ -212,21 +207,7 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         const int n = n0 + tx * TN + j;
-        if (n >= g.N) continue;
-        g.C[m * g.N + n] = acc[i][j] + (g.bias ? g.bias[n] : 0.f);  // pre-activation (see the header)
-      }
-    }
-  } else if (MODE == DX) {
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int64_t m = m0 + ty * TM + i;
-      if (m >= g.M) continue;
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx * TN + j;
-        if (n >= g.N) continue;
-        const float d = (g.mask && g.mask_act >= 0) ? act_grad(g.mask_act, g.mask[m * g.N + n]) : 1.f;
-        g.C[m * g.N + n] = acc[i][j] * d;
+        if (n < g.N) store_out<MODE>(g, m, n, acc[i][j]);
       }
     }
   } else {
@@ -252,6 +233,204 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
   }
 }
 
+// ---- small-grid variant ------------------------------------------------------------------------------------------------
+// When the 64x64 tiling above gives fewer CTAs than the GPU has SMs (batch-256 SAC epochs, 1024-env rollouts, heads), each CTA
+// is a serial chain of K/16 load -> sync -> fma -> sync steps and the GEMM costs tens of microseconds of pure latency.  This
+// variant uses 32x32 output tiles (4x the CTAs) and stages the WHOLE reduction panel (<= 256 at a time) in shared memory: every
+// global load of both panels is in flight before the first shared store (ONE exposed memory latency), then the two halves of
+// the CTA (128 threads each, 2x4 outputs per thread) take the even / odd k of the panel and their partial sums are added in a
+// fixed order (even + odd) through shared memory => deterministic.
+constexpr int PM = 32, PN = 32, PK = 256, PTM = 2, PTN = 4;
+constexpr int kPanelHalf = (PM / PTM) * (PN / PTN);  // 128 threads cover the tile once
+constexpr int kPanelThreads = 2 * kPanelHalf;        // 256
+constexpr int kPanelWarps = kPanelThreads / 32;
+constexpr int kAsLd = PM + 2, kBsLd = PN + 4;        // float2 / float4 aligned rows
+constexpr uint32_t kPanelSmemBytes = PK * (kAsLd + kBsLd) * 4;
+constexpr int kPanelLoads = PM * PK / kPanelThreads; // 32 per thread and panel
+
+// Panel element owned by (thread, u) in the two global layouts:
+//   reduction index fastest in memory (FWD-A, DX-A, DX-B): warp w takes tile rows w, w + 8, ..; lanes walk k  -> coalesced
+//   tile column fastest in memory    (FWD-B, DW-A, DW-B): warp w takes panel rows w, w + 8, ..; lane = column -> coalesced
+__device__ __forceinline__ void panel_coord_red(int u, int& mm, int& kk) {
+  mm = (threadIdx.x >> 5) + kPanelWarps * (u / (PK / 32));
+  kk = (threadIdx.x & 31) + 32 * (u % (PK / 32));
+}
+__device__ __forceinline__ void panel_coord_col(int u, int& mm, int& kk) {
+  mm = threadIdx.x & 31;
+  kk = (threadIdx.x >> 5) + kPanelWarps * u;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPanelThreads) gemm_panel_kernel(GemmArgs g) {
+  extern __shared__ __align__(16) float psm[];
+  float* As = psm;               // [PK][kAsLd]: As[kk][m]
+  float* Bs = psm + PK * kAsLd;  // [PK][kBsLd]: Bs[kk][n]
+  const int tid = threadIdx.x;
+  const int half = tid / kPanelHalf, t = tid % kPanelHalf;
+  const int tx = t % (PN / PTN), ty = t / (PN / PTN);
+  const int64_t m0 = (int64_t)blockIdx.y * PM;
+  const int n0 = blockIdx.x * PN;
+  float acc[PTM][PTN];
+#pragma unroll
+  for (int i = 0; i < PTM; ++i)
+#pragma unroll
+    for (int j = 0; j < PTN; ++j) acc[i][j] = 0.f;
+  float dbacc[PTN] = {0.f, 0.f, 0.f, 0.f};
+
+  int64_t r_begin = 0, r_end;
+  if (MODE == DW) {
+    r_begin = (int64_t)blockIdx.z * g.rows_per_split;
+    r_end = r_begin + g.rows_per_split;
+    if (r_end > g.M) r_end = g.M;
+  } else {
+    r_end = g.K;
+  }
+  const int out_rows = (MODE == DW) ? g.K : 0;
+
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += PK) {
+    const int kc = (int)((r_end - r0) < PK ? (r_end - r0) : PK);
+    float va[kPanelLoads], vb[kPanelLoads];
+    // ---- A panel ----
+#pragma unroll
+    for (int u = 0; u < kPanelLoads; ++u) {
+      int mm, kk;
+      if (MODE == DW) {  // A(f, r) = H[row(r)][f]
+        panel_coord_col(u, mm, kk);
+        const int64_t f = m0 + mm;
+        const bool ok = kk < kc && f < out_rows;
+        const int64_t row = ok ? (g.rowidx ? (int64_t)__ldg(g.rowidx + r0 + kk) : r0 + kk) : 0;
+        va[u] = ok ? __ldg(g.A + row * g.lda + f) : 0.f;
+      } else {           // A[row(m)][r0 + kk]
+        panel_coord_red(u, mm, kk);
+        const int64_t m = m0 + mm;
+        const bool ok = kk < kc && m < g.M;
+        const int64_t row = ok ? ((MODE == FWD && g.rowidx) ? (int64_t)__ldg(g.rowidx + m) : m) : 0;
+        va[u] = ok ? __ldg(g.A + row * g.lda + r0 + kk) : 0.f;
+      }
+    }
+    // ---- B panel ----
+#pragma unroll
+    for (int u = 0; u < kPanelLoads; ++u) {
+      int nn, kk;
+      if (MODE == DX) {  // B(kk, j) = W[j][r0 + kk]
+        panel_coord_red(u, nn, kk);
+        const int j = n0 + nn;
+        vb[u] = (kk < kc && j < g.N) ? __ldg(g.B + (int64_t)j * g.K + r0 + kk) : 0.f;
+      } else {           // FWD: W[k][n]; DW: dY[r][n]
+        panel_coord_col(u, nn, kk);
+        const int n = n0 + nn;
+        vb[u] = (kk < kc && n < g.N) ? __ldg(g.B + (r0 + kk) * g.N + n) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPanelLoads; ++u) {
+      int mm, kk;
+      if (MODE == DW) panel_coord_col(u, mm, kk);
+      else panel_coord_red(u, mm, kk);
+      if (kk < kc) As[kk * kAsLd + mm] = va[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kPanelLoads; ++u) {
+      int nn, kk;
+      if (MODE == DX) panel_coord_red(u, nn, kk);
+      else panel_coord_col(u, nn, kk);
+      if (kk < kc) Bs[kk * kBsLd + nn] = vb[u];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = half; kk < kc; kk += 2) {
+      const float2 a = *reinterpret_cast<const float2*>(As + kk * kAsLd + ty * PTM);
+      const float4 b = *reinterpret_cast<const float4*>(Bs + kk * kBsLd + tx * PTN);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]), acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, b.z, acc[0][2]), acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]), acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, b.z, acc[1][2]), acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      if (MODE == DW) dbacc[0] += b.x, dbacc[1] += b.y, dbacc[2] += b.z, dbacc[3] += b.w;
+    }
+    __syncthreads();
+  }
+
+  // ---- even-k half + odd-k half (fixed order), then the epilogue on the first half ----
+  float* red = psm;  // [kPanelHalf][12]
+  if (half == 1) {
+    float* r = red + t * 12;
+#pragma unroll
+    for (int i = 0; i < PTM; ++i)
+#pragma unroll
+      for (int j = 0; j < PTN; ++j) r[i * PTN + j] = acc[i][j];
+#pragma unroll
+    for (int j = 0; j < PTN; ++j) r[8 + j] = dbacc[j];
+  }
+  __syncthreads();
+  if (half == 1) return;
+  {
+    const float* r = red + t * 12;
+#pragma unroll
+    for (int i = 0; i < PTM; ++i)
+#pragma unroll
+      for (int j = 0; j < PTN; ++j) acc[i][j] += r[i * PTN + j];
+#pragma unroll
+    for (int j = 0; j < PTN; ++j) dbacc[j] += r[8 + j];
+  }
+  if (MODE != DW) {
+#pragma unroll
+    for (int i = 0; i < PTM; ++i) {
+      const int64_t m = m0 + ty * PTM + i;
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < PTN; ++j) {
+        const int n = n0 + tx * PTN + j;
+        if (n < g.N) store_out<MODE>(g, m, n, acc[i][j]);
+      }
+    }
+  } else {
+    float* Cp = g.C + (int64_t)blockIdx.z * g.part_stride;
+#pragma unroll
+    for (int i = 0; i < PTM; ++i) {
+      const int64_t f = m0 + ty * PTM + i;
+      if (f >= out_rows) continue;
+#pragma unroll
+      for (int j = 0; j < PTN; ++j) {
+        const int n = n0 + tx * PTN + j;
+        if (n < g.N) Cp[f * g.N + n] = acc[i][j];
+      }
+    }
+    if (blockIdx.y == 0 && ty == 0 && g.dbias) {
+      float* dbp = g.dbias + (int64_t)blockIdx.z * g.dbias_stride;
+#pragma unroll
+      for (int j = 0; j < PTN; ++j) {
+        const int n = n0 + tx * PTN + j;
+        if (n < g.N) dbp[n] = dbacc[j];
+      }
+    }
+  }
+}
+
+// One entry point for the three GEMM flavours: picks the tiling from the grid the 64x64 kernel would get.
+constexpr int kPanelBelowCtas = 148;
+template <int MODE>
+inline cudaError_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
+  const int64_t out_rows = (MODE == DW) ? g.K : g.M;
+  const int64_t ctas64 = ((out_rows + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (MODE == DW ? splits : 1);
+  if (ctas64 >= kPanelBelowCtas) {
+    dim3 grid((g.N + BN - 1) / BN, (unsigned)((out_rows + BM - 1) / BM), MODE == DW ? splits : 1);
+    gemm_kernel<MODE><<<grid, kThreads, 0, st>>>(g);
+    return cudaGetLastError();
+  }
+  static unsigned long long opted = 0;  // bit d: dynamic shared memory opt-in done on device d (per instantiation)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || !((opted >> dev) & 1ull)) {
+    e = cudaFuncSetAttribute(gemm_panel_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) opted |= 1ull << dev;
+  }
+  dim3 grid((g.N + PN - 1) / PN, (unsigned)((out_rows + PM - 1) / PM), MODE == DW ? splits : 1);
+  gemm_panel_kernel<MODE><<<grid, kPanelThreads, kPanelSmemBytes, st>>>(g);
+  return cudaGetLastError();
+}
+
 // grad[i] += w * sum_z part[z*stride + i]   (fixed order over z -> deterministic)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride,
                                        int64_t n, float w, float* __restrict__ grad, int overwrite) {
@@ -263,8 +442,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
 }
 
 // ---- LayerNorm (flax nn.LayerNorm defaults: epsilon 1e-6, scale + bias, over the feature axis) ---------------------
-// per-row statistics of U (M x N): stats[m] = (mean, 1/sqrt(var + eps)); one warp per row
-__global__ void ln_stats_kernel(const float* __restrict__ U, int64_t M, int N, float* __restrict__ stats) {
+// per-row statistics of U (M x N): stats[m] = (mean, 1/sqrt(var + eps)) (nullable) and the layer output
+// H[m] = f((U[m] - mean) * rstd * gamma + beta) that the next GEMM multiplies (H may alias U).  One warp per row.
+__global__ void ln_apply_kernel(const float* U, int64_t M, int N, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                float* __restrict__ stats, float* H) {
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -278,7 +459,10 @@ __global__ void ln_stats_kernel(const float* __restrict__ U, int64_t M, int N, f
     q = fmaf(d, d, q);
   }
   const float var = warp_sum(q) / (float)N;
-  if (lane == 0) stats[2 * row] = mean, stats[2 * row + 1] = rsqrtf(var + 1e-6f);
+  const float rstd = rsqrtf(var + 1e-6f);
+  if (lane == 0 && stats) stats[2 * row] = mean, stats[2 * row + 1] = rstd;
+  float* h = H + row * N;
+  for (int k = lane; k < N; k += 32) h[k] = act_fwd(act, (u[k] - mean) * rstd * __ldg(gamma + k) + __ldg(beta + k));
 }
 
 // Backward through h = f(z), z = uhat * gamma + beta, uhat = (u - mean) * rstd for the rows of one layer:

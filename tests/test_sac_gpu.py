@@ -217,18 +217,21 @@ def test_learning_moves_towards_the_optimum():
     from stoix_b200.utils.total_timestep_checker import check_total_timesteps
 
     torch.cuda.set_device(0)
-    cfg = _cfg(["arch.total_num_envs=256", "arch.total_timesteps=153600", "arch.num_evaluation=3", "system.actor_lr=1e-3", "system.q_lr=1e-3",
-                "system.gamma=0.0"])
+    # fixed small temperature: with alpha = 1 the entropy term (|log_prob| ~ 6) swamps a reward of magnitude < 1
+    cfg = _cfg(["arch.total_num_envs=256", "arch.total_timesteps=768000", "arch.num_evaluation=3", "system.actor_lr=1e-3", "system.q_lr=1e-3",
+                "system.gamma=0.0", "system.autotune=False", "system.init_alpha=0.01"])
     cfg.num_devices, cfg.rank = 1, 0
     cfg = check_total_timesteps(cfg, quiet=True)
     env, _ = environments.make(cfg)
-    learn, _, state = ff_sac.learner_setup(env, tuple(srandom.split(srandom.PRNGKey(0), 3)), cfg)
+    learn, actor_network, state = ff_sac.learner_setup(env, tuple(srandom.split(srandom.PRNGKey(0), 3)), cfg)
     rewards = []
+    rewards.append(float(env.step(state.env_state[0], actor_network.apply(state.params.actor_params, state.timestep[0].observation).sample(seed=1))[1]
+                         .reward.mean()))
     for _ in range(3):
         out = learn(state)
         state = out.learner_state
-        rewards.append(float(learn.built["shards"][0].reward.mean()))
-    assert np.isfinite(rewards).all() and rewards[-1] > rewards[0] + 0.05, rewards
+        rewards.append(float(out.episode_metrics["episode_return"].sum() * 0 + learn.built["shards"][0].reward.mean()))
+    assert np.isfinite(rewards).all() and rewards[-1] > rewards[0] + 0.1, rewards
     assert learn.built["graph"] is not None
     st = learn.built["shards"][0].buffer.ring.state.cpu().tolist()
     assert st[1] == min(4096, (4 + 3 * cfg.arch.num_updates_per_eval) * 256)
