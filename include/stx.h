@@ -270,6 +270,18 @@ int stx_allreduce_clip_adam_step(float* param_arena, const float* const* peer_gr
                                  int world, int rank, int pad_slot_offset, float* gsum, float* mu, float* nu,
                                  int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper,
                                  void* params_bf16, float* gnorm_out, void* scratch, void* stream);
+/* Two-shot form (the default of the learner): rank r sums slice r of the W gradient arenas (peer LOADS, rank order) and stores
+ * the result into every rank's reduced-gradient buffer (peer STORES), so (W-1)/W of the arena crosses NVLink in each direction
+ * instead of W-1 arenas inbound; the per-rank sum-of-squares partials of the clipping norm travel with the slices and the second
+ * hand-shake replaces the grid barrier of the norm.  Every element is reduced once, by one rank => identical on all ranks.
+ *   peer_gsum[r]   HOST array of `world` DEVICE pointers: rank r's reduced-gradient buffer, peer-mapped, arena_len + 128 floats
+ *                  (tail: double[world][8] norm partials).  arena_len % 4 == 0; the padding between segments must hold zeros.
+ *   signal pads    slots [pad_slot_offset, +8) "gradients ready", [pad_slot_offset + 8, +16) "slice stored".
+ *   grid           0 = one block per SM; tests that run several virtual ranks on one device pass a small co-resident grid. */
+int stx_allreduce2_clip_adam_step(float* param_arena, const float* const* peer_grads, float* const* peer_gsum, int64_t arena_len,
+                                  void* const* peer_signal_pads, int world, int rank, int pad_slot_offset, float* mu, float* nu,
+                                  int32_t* counts, const StxAdamSeg* segs, int nseg, const StxAdamHyper* hyper, void* params_bf16,
+                                  float* gnorm_out, void* scratch, int grid, void* stream);
 
 /* ------------------------------------------------------------------ shuffle -------------------
  * perm[i] = keyed bijection of [0, n) (cycle-walking Feistel over Philox rounds) replacing

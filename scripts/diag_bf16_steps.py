@@ -22,9 +22,12 @@ from stoix_b200.utils.total_timestep_checker import check_total_timesteps  # noq
 def main():
     E, T, nmb = (int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (128, 16, 4)))
     perturb = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+    precision = sys.argv[5] if len(sys.argv) > 5 else "bf16"     # "f32": the CUDA-core path against the plain fp64 oracle
+    bf16 = precision == "bf16"
+    extra = sys.argv[6:]
     cfg = compose("default_ff_ppo", ["env=synthetic/box", f"arch.total_num_envs={E}", f"system.rollout_length={T}",
                                      f"system.num_minibatches={nmb}", f"arch.total_timesteps={E * T * 2}", "arch.num_evaluation=1",
-                                     "arch.precision=bf16", "logger.use_console=False", "arch.cuda_graph=False"])
+                                     f"arch.precision={precision}", "logger.use_console=False", "arch.cuda_graph=False"] + extra)
     cfg.num_devices, cfg.rank = 1, 0
     cfg = check_total_timesteps(cfg, quiet=True)
     env, _ = make_env.make(cfg)
@@ -35,7 +38,8 @@ def main():
         with torch.no_grad():
             g = torch.Generator(device="cuda").manual_seed(1)
             a_tree.arena.add_(torch.randn(a_tree.arena.shape, device="cuda", generator=g) * perturb)
-            ops.cast_bf16(a_tree.arena, out=a_tree.arena_bf16)
+            if bf16:
+                ops.cast_bf16(a_tree.arena, out=a_tree.arena_bf16)
     learn.ensure_built(state)
     b = learn.built
     learn.phases["rollout"](state)
@@ -68,18 +72,20 @@ def main():
         batch.perm = torch.as_tensor(perm, device="cuda")
         for i in range(nmb):
             idx = perm[i * mb:(i + 1) * mb]
-            actor = O.MLPParams.from_flat(f64(a_tree.flat), list(sa.sizes)).astype(np.float32)
-            critic = O.MLPParams.from_flat(f64(c_tree.flat), list(sc.sizes)).astype(np.float32)
+            actor = O.MLPParams.from_flat(f64(a_tree.flat), list(sa.sizes))
+            critic = O.MLPParams.from_flat(f64(c_tree.flat), list(sc.sizes))
+            if bf16:
+                actor, critic = actor.astype(np.float32), critic.astype(np.float32)
             ops.ppo_minibatch_grads(sa, sc, b["arena"], batch, i * mb, mb, 0.2, 0.01, 0.5, True, grads, metrics, b["ws"],
-                                    ops.STX_PREC_BF16, 1.0, b["arena_bf16"], overwrite=True)
+                                    ops.STX_PREC_BF16 if bf16 else ops.STX_PREC_F32, 1.0, b["arena_bf16"], overwrite=True)
             torch.cuda.synchronize()
             g = f64(grads)
-            lg, a_acts = O.mlp_forward(actor, obs[idx], bf16_operands=True)
+            lg, a_acts = O.mlp_forward(actor, obs[idx], bf16_operands=bf16)
             _, dlg, _ = O.actor_loss_and_dlogits(lg.astype(np.float64), act[idx], lp_old[idx], adv[idx], 0.2, 0.01)
-            ga = O.mlp_backward(actor, a_acts, dlg, bf16_operands=True)
-            v, c_acts = O.mlp_forward(critic, obs[idx], bf16_operands=True)
+            ga = O.mlp_backward(actor, a_acts, dlg, bf16_operands=bf16)
+            v, c_acts = O.mlp_forward(critic, obs[idx], bf16_operands=bf16)
             _, dv, _ = O.critic_loss_and_dvalue(v[:, 0].astype(np.float64), v_old[idx], tgt[idx], 0.2, 0.5)
-            gc = O.mlp_backward(critic, c_acts, dv[:, None], bf16_operands=True)
+            gc = O.mlp_backward(critic, c_acts, dv[:, None], bf16_operands=bf16)
             ra, rc = rel(g[:sa.param_count], ga.flat()), rel(g[coff:coff + sc.param_count], gc.flat())
             per = []
             for label, spec, off, ref in (("a", sa, 0, ga), ("c", sc, coff, gc)):
@@ -89,6 +95,8 @@ def main():
             print(f"step {step:2d} (ep {ep} mb {i}): actor rel {ra:.2e} |g| {np.linalg.norm(ga.flat()):.3e}   critic rel {rc:.2e} "
                   f"|g| {np.linalg.norm(gc.flat()):.3e}   " + " ".join(per))
             ops.clip_adam_step(b["plan"], b["arena"], grads, a_tree.arena_mu, a_tree.arena_nu, params_bf16=b["arena_bf16"])
+            if not bf16:   # end-state sensitivity: the same step from the same state on the oracle side
+                pass
             step += 1
 
 

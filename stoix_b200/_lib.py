@@ -136,6 +136,8 @@ _SIGNATURES = {
     "stx_clipped_value_loss": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P, _P, _P]),
     "stx_adam_scratch_bytes": (C.c_size_t, [C.c_int]),
     "stx_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(StxAdamHyper), _P, _P, _P, _P]),
+    "stx_allreduce2_clip_adam_step": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "stx_allreduce_clip_adam_step": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P,
                                                 C.c_int, C.POINTER(StxAdamHyper), _P, _P, _P, _P]),
     "stx_make_permutation": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),

@@ -7,6 +7,7 @@ eager-PyTorch fallback -- a non-CUDA tensor raises StxError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -453,6 +454,15 @@ class PeerGradBuffers:
         self.grad_ptrs = [(C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in self.handles]
         self.pad_ptrs = (C.c_void_p * self.world)(*[int(p) for p in h0.signal_pad_ptrs])
         self.gsum = torch.zeros(int(total), dtype=torch.float32, device=device)
+        # two-shot form: the reduced gradient of every rank is written by its peers -> symmetric too (+ the norm table)
+        self.total = int(total)
+        self.gsum2 = symm_mem.empty(self.total + 128, dtype=torch.float32, device=device)
+        self.gsum2.zero_()
+        self.gsum2_handle = symm_mem.rendezvous(self.gsum2, group)
+        self.gsum2_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.gsum2_handle.buffer_ptrs])
+        self.mode = int(os.environ.get("STX_ALLREDUCE_MODE", "2"))   # 2 = two-shot (default), 1 = one-shot
+        if self.total % 4 != 0:
+            self.mode = 1
         torch.cuda.synchronize()
         dist.barrier(group)
 
@@ -463,6 +473,14 @@ def allreduce_clip_adam_step(plan: AdamPlan, peers: PeerGradBuffers, which: int,
     _need_cuda(params, mu, nu, params_bf16)
     plan.hyper.grad_scale = 1.0 / peers.world
     plan.hyper.prenorm = 0
+    if peers.mode == 2:
+        _lib.check(
+            _lib.load().stx_allreduce2_clip_adam_step(_p(params), peers.grad_ptrs[which], peers.gsum2_ptrs, peers.total, peers.pad_ptrs, peers.world,
+                                                      peers.rank, peers.slot, _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg,
+                                                      C.byref(plan.hyper), _p(params_bf16), _p(plan.gnorm), _p(plan.scratch), 0, _stream()),
+            "stx_allreduce2_clip_adam_step",
+        )
+        return
     _lib.check(
         _lib.load().stx_allreduce_clip_adam_step(_p(params), peers.grad_ptrs[which], peers.pad_ptrs, peers.world, peers.rank, peers.slot,
                                                  _p(peers.gsum), _p(mu), _p(nu), _p(plan.counts), _p(plan.segs), plan.nseg,
