@@ -42,8 +42,8 @@ def bench(T, E, quads=0, iters=20, flush=True):
 
 if __name__ == "__main__":
     out = []
-    for (T, E) in [(128, 4096), (128, 65536), (128, 1048576)]:
-        for q in (0, 32, 416, 408, 316):
+    for (T, E) in [(128, 4096), (128, 32768), (128, 65536), (128, 262144), (128, 1048576), (256, 524288), (128, 4194304)]:
+        for q in (0, 500, 501, 502, 416):   # 0 = the shipped heuristic, 500 / 501 = TMA-pipelined 32x128 / 64x64 tiles, 416 = 2 x 512 threads
             for fl in (True,):
                 out.append(bench(T, E, q, flush=fl))
                 print(json.dumps(out[-1]), flush=True)
