@@ -399,11 +399,33 @@ bool gae_make_map(CUtensorMap* m, const void* base, int T, int E, bool f32, int 
 template <int kGE, int kGT>
 int launch_gae_tma_shape(const PpoIn& in, int T, int E, int want, float* adv, float* tgt, float* stats, double2* partials, unsigned int* counter,
                          cudaStream_t st) {
-  CUtensorMap mr, mv, mvt, mdn, mtr;
-  if (!(gae_make_map(&mr, in.reward, T, E, true, kGE, kGT) && gae_make_map(&mv, in.v_tm1, T, E, true, kGE, kGT) &&
-        gae_make_map(&mvt, in.v_t, T, E, true, kGE, kGT) && gae_make_map(&mdn, in.done, T, E, false, kGE, kGT) &&
-        gae_make_map(&mtr, in.trunc, T, E, false, kGE, kGT)))
-    return 1;
+  // the five tensor maps depend on (pointers, T, E) only: keep the last few sets (encoding them costs ~10 us of host time per map,
+  // during which an eager caller leaves the GPU idle; a captured graph bakes them in anyway)
+  struct MapSet {
+    const void* key[5];
+    int T, E;
+    CUtensorMap m[5];
+    bool valid;
+  };
+  static thread_local MapSet cache[4] = {};
+  static thread_local int next_slot = 0;
+  const void* key[5] = {in.reward, in.v_tm1, in.v_t, in.done, in.trunc};
+  MapSet* ms = nullptr;
+  for (auto& c : cache)
+    if (c.valid && c.T == T && c.E == E && c.key[0] == key[0] && c.key[1] == key[1] && c.key[2] == key[2] && c.key[3] == key[3] && c.key[4] == key[4])
+      ms = &c;
+  if (!ms) {
+    MapSet fresh{};
+    for (int i = 0; i < 5; ++i) {
+      fresh.key[i] = key[i];
+      if (!gae_make_map(&fresh.m[i], key[i], T, E, i < 3, kGE, kGT)) return 1;
+    }
+    fresh.T = T, fresh.E = E, fresh.valid = true;
+    ms = &cache[next_slot];
+    next_slot = (next_slot + 1) % 4;
+    *ms = fresh;
+  }
+  const CUtensorMap &mr = ms->m[0], &mv = ms->m[1], &mvt = ms->m[2], &mdn = ms->m[3], &mtr = ms->m[4];
   static unsigned long long opted = 0;
   int dev = 0;
   STX_CUDA_OK(cudaGetDevice(&dev));
