@@ -411,6 +411,31 @@ int stx_replay_sample(const StxReplay* rb, int64_t M, uint64_t seed, uint64_t of
                       float* xq_old, float* xq_new, float* xq_next, int64_t ld, float* reward, uint8_t* done, int32_t* idx_out,
                       void* stream);
 
+/* ------------------------------------------------------------------ recurrent PPO building blocks (fp32) ------
+ * stx_gru_sequence_forward / _backward: ScannedRNN(cell_type="gru") (stoix/networks/base.py:124-159; flax.linen.GRUCell) over a
+ *   (T, E) sequence with episode resets, as RecurrentActor / RecurrentCritic run it (base.py:162-222) one step at a time in the
+ *   rollout (rec_ppo.py:90-101, T = 1) and over a whole chunk inside the losses (rec_ppo.py:216-247, under jax.grad).
+ *     gi     [T][E][3H]  input projections W_i x + b_i of all steps (columns r | z | n): the head of the pre-torso MLP
+ *     reset  [T][E]      the carry entering step t is replaced by zeros where set (done | truncated of the PREVIOUS transition)
+ *     h0     [E][H], w_h [H][3H] (columns r | z | n), b_hn [H];  h_seq [T][E][H] = the cell outputs (= new carries)
+ *   backward: d_h_seq = d(loss)/d(h_t) from the layers above; writes d_gi [T][E][3H]; d_w_h / d_b_hn (nullable pair) receive
+ *   grad_weight * gradient (added unless overwrite); d_h0 nullable.  `workspace` (stx_gru_workspace_bytes) carries the saved gates
+ *   from forward to backward.
+ * stx_ppo_head_grads: _actor_loss_fn / _critic_loss_fn (rec_ppo.py:207-257, same losses as ff_ppo.py:191-235) on network outputs
+ *   already computed: d(loss)/d(logits) and / or d(loss)/d(value) + the loss metrics (actor_loss, entropy, value_loss, mean
+ *   advantage, mean value, mean target; accumulated with `weight`).  Row m of logits / value pairs with row idx[m] (or row0 + m) of the
+ *   batch arrays.  scratch: stx_ppo_head_scratch_bytes(mb), zeroed once. */
+size_t stx_gru_workspace_bytes(int T, int64_t E, int H);
+int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, const float* h0, const float* w_h, const float* b_hn, int T, int64_t E, int H,
+                             float* h_seq, void* workspace, size_t workspace_bytes, void* stream);
+int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* reset, const float* w_h, int T, int64_t E, int H, void* workspace,
+                              size_t workspace_bytes, float* d_gi, float* d_w_h, float* d_b_hn, float grad_weight, int overwrite, float* d_h0,
+                              void* stream);
+size_t stx_ppo_head_scratch_bytes(int64_t mb);
+int stx_ppo_head_grads(const float* logits, const float* value, const int32_t* idx, int64_t row0, const int32_t* action, const float* logp_old,
+                       const float* v_old, const float* adv, const float* targets, const float* adv_stats, int64_t mb, int A, float clip_eps,
+                       float ent_coef, float vf_coef, float* d_logits, float* d_value, float* metrics, float weight, void* scratch, void* stream);
+
 /* Utility casts used by the bf16 path (obs / weight shadows). */
 int stx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -330,6 +330,34 @@ extern "C" int stx_mlp_backward(const StxMlp* m, const float* x, int64_t ldx, co
   return simt_backward(m, x, ldx, row_idx, M, ws, grad_weight, net_grad, overwrite, st, d_input);
 }
 
+// ---- PPO loss heads on precomputed network outputs (the recurrent system runs its networks outside the fused PPO kernels) ----
+extern "C" size_t stx_ppo_head_scratch_bytes(int64_t mb) { return 256 + (size_t)((mb + 255) / 256) * 6 * sizeof(double); }
+
+extern "C" int stx_ppo_head_grads(const float* logits, const float* value, const int32_t* idx, int64_t row0, const int32_t* action,
+                                  const float* logp_old, const float* v_old, const float* adv, const float* targets, const float* adv_stats,
+                                  int64_t mb, int A, float clip_eps, float ent_coef, float vf_coef, float* d_logits, float* d_value, float* metrics,
+                                  float weight, void* scratch, void* stream) {
+  STX_REQUIRE((logits || value) && action && logp_old && v_old && adv && targets && metrics && scratch && mb > 0, STX_E_ARG,
+              "stx_ppo_head_grads: null pointer or mb=%lld", (long long)mb);
+  STX_REQUIRE(!logits || (d_logits && A > 0 && A <= kMaxActions), STX_E_SHAPE, "stx_ppo_head_grads: A=%d (max %d) / null d_logits", A, kMaxActions);
+  STX_REQUIRE(!value || d_value, STX_E_ARG, "stx_ppo_head_grads: null d_value");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int pass = 0; pass < 2; ++pass) {  // actor then critic: each is one launch of the kernel the fused fp32 path uses
+    if ((pass == 0 && !logits) || (pass == 1 && !value)) continue;
+    LossArgs g{};
+    g.logits = pass == 0 ? logits : nullptr, g.value = pass == 1 ? value : nullptr, g.value_ld = 1, g.idx = idx, g.row0 = row0;
+    g.action = action, g.logp_old = logp_old, g.v_old = v_old, g.adv = adv, g.tgt = targets, g.adv_stats = adv_stats;
+    g.dlogits = d_logits, g.dvalue = d_value, g.mb = mb, g.A = pass == 0 ? A : 0;
+    g.clip_eps = clip_eps, g.ent_coef = ent_coef, g.vf_coef = vf_coef;
+    g.counter = reinterpret_cast<unsigned int*>(scratch);
+    g.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    g.metrics = metrics, g.weight = weight;
+    ppo_loss_grad_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, st>>>(g);
+    STX_LAUNCH_OK();
+  }
+  return STX_OK;
+}
+
 extern "C" int stx_categorical(const float* logits, int64_t E, int A, int sample, uint64_t seed,
                                uint64_t offset, const uint64_t* dev_counter, int32_t* action,
                                float* log_prob, float* entropy, void* stream) {

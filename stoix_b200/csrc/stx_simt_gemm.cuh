@@ -432,7 +432,7 @@ inline cudaError_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
 }
 
 // grad[i] += w * sum_z part[z*stride + i]   (fixed order over z -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride,
+static __global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride,
                                        int64_t n, float w, float* __restrict__ grad, int overwrite) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -444,7 +444,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
 // ---- LayerNorm (flax nn.LayerNorm defaults: epsilon 1e-6, scale + bias, over the feature axis) ---------------------
 // per-row statistics of U (M x N): stats[m] = (mean, 1/sqrt(var + eps)) (nullable) and the layer output
 // H[m] = f((U[m] - mean) * rstd * gamma + beta) that the next GEMM multiplies (H may alias U).  One warp per row.
-__global__ void ln_apply_kernel(const float* U, int64_t M, int N, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+static __global__ void ln_apply_kernel(const float* U, int64_t M, int N, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                 float* __restrict__ stats, float* H) {
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -473,7 +473,7 @@ __global__ void ln_apply_kernel(const float* U, int64_t M, int N, const float* _
 // warp order -> part[block][2N], reduced over blocks in a fixed order by reduce_partials_kernel: deterministic.
 // D (M x N) holds dh on entry and du on exit.  N <= 32 * kLnMaxCols.
 constexpr int kLnWarps = 8, kLnMaxCols = 32;
-__global__ void __launch_bounds__(32 * kLnWarps) ln_backward_kernel(float* __restrict__ D, const float* __restrict__ U,
+static __global__ void __launch_bounds__(32 * kLnWarps) ln_backward_kernel(float* __restrict__ D, const float* __restrict__ U,
                                                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, int act, int64_t M, int N,
                                                                   int rows_per_block, float* __restrict__ part) {

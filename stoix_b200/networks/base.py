@@ -168,3 +168,11 @@ class MultiNetwork:
         return torch.stack([n.apply(p, *network_input) for n, p in zip(self.networks, params)], dim=-1)
 
     __call__ = apply
+
+
+def __getattr__(name):   # stoix.networks.base.{ScannedRNN, RecurrentActor, RecurrentCritic} (base.py:124-222) live in recurrent.py
+    if name in ("ScannedRNN", "RecurrentActor", "RecurrentCritic"):
+        from . import recurrent
+
+        return getattr(recurrent, name)
+    raise AttributeError(name)

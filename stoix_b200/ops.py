@@ -623,34 +623,37 @@ def mlp_train_workspace(spec: MlpSpec, M: int, device) -> torch.Tensor:
     return torch.zeros(int(_lib.load().stx_mlp_train_workspace_bytes(C.byref(m), int(M))), dtype=torch.uint8, device=device)
 
 
-def mlp_forward_train(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, ws: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Forward that keeps the torso pre-activations (and LayerNorm statistics) in `ws` for mlp_backward.  x (M, >= in_dim)
-    float32, rows may be wider than the input dim (leading dimension x.stride(0))."""
-    dev = _need_cuda(params, ws, out)
+def mlp_forward_train(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, ws: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      row_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Forward that keeps the torso pre-activations (and LayerNorm statistics) in `ws` for mlp_backward.  x (rows, >= in_dim)
+    float32, rows may be wider than the input dim (leading dimension x.stride(0)); row_idx (int32, M): batch row m = x[row_idx[m]]."""
+    dev = _need_cuda(params, ws, out, row_idx)
     if not x.is_cuda or x.dtype != torch.float32 or x.ndim != 2 or x.stride(1) != 1 or x.shape[1] < spec.sizes[0]:
         raise StxError("mlp_forward_train: x must be a CUDA float32 matrix with unit column stride and >= in_dim columns")
-    M = int(x.shape[0])
+    if row_idx is not None and row_idx.dtype != torch.int32:
+        raise StxError("mlp_forward_train: row_idx must be int32")
+    M = int(row_idx.numel()) if row_idx is not None else int(x.shape[0])
     if out is None:
         out = torch.empty((M, spec.sizes[-1]), dtype=torch.float32, device=dev)
     m = spec.c_struct(params)
-    _lib.check(_lib.load().stx_mlp_forward_train(C.byref(m), _p(x), x.stride(0), None, M, _p(out), _p(ws), ws.numel(), _stream()),
+    _lib.check(_lib.load().stx_mlp_forward_train(C.byref(m), _p(x), x.stride(0), _p(row_idx), M, _p(out), _p(ws), ws.numel(), _stream()),
                "stx_mlp_forward_train")
     return out
 
 
 def mlp_backward(spec: MlpSpec, params: torch.Tensor, x: torch.Tensor, d_out: torch.Tensor, ws: torch.Tensor,
                  net_grad: Optional[torch.Tensor] = None, grad_weight: float = 1.0, overwrite: bool = True,
-                 d_input: Optional[torch.Tensor] = None) -> None:
+                 d_input: Optional[torch.Tensor] = None, row_idx: Optional[torch.Tensor] = None) -> None:
     """Backward of the forward that filled `ws`: parameter gradients into net_grad (layout of the parameter arena) and / or
     d(loss)/d(input) into d_input (M, in_dim) dense."""
-    _need_cuda(params, d_out, ws, net_grad, d_input)
-    M = int(x.shape[0])
+    _need_cuda(params, d_out, ws, net_grad, d_input, row_idx)
+    M = int(row_idx.numel()) if row_idx is not None else int(x.shape[0])
     if d_out.dtype != torch.float32 or d_out.numel() != M * spec.sizes[-1]:
         raise StxError("mlp_backward: d_out must be float32 (M, out_dim)")
     if d_input is not None and (d_input.dtype != torch.float32 or d_input.numel() != M * spec.sizes[0]):
         raise StxError("mlp_backward: d_input must be float32 (M, in_dim)")
     m = spec.c_struct(params)
-    _lib.check(_lib.load().stx_mlp_backward(C.byref(m), _p(x), x.stride(0), None, M, _p(d_out), _p(ws), ws.numel(), float(grad_weight),
+    _lib.check(_lib.load().stx_mlp_backward(C.byref(m), _p(x), x.stride(0), _p(row_idx), M, _p(d_out), _p(ws), ws.numel(), float(grad_weight),
                                             _p(net_grad), int(bool(overwrite)), _p(d_input), _stream()), "stx_mlp_backward")
 
 
@@ -778,3 +781,57 @@ def replay_sample(rb: ReplayRing, M: int, seed: int, xq_old: torch.Tensor, rewar
             raise StxError("replay_sample: xq_* must be float32 (M, >= obs_dim + act_dim) with one common leading dimension")
     _lib.check(_lib.load().stx_replay_sample(C.byref(rb.c), int(M), int(seed) & (2**64 - 1), int(offset), _p(dev_counter), _p(idx_in), _p(xq_old),
                                              _p(xq_new), _p(xq_next), int(ld), _p(reward), _p(done), _p(idx_out), _stream()), "stx_replay_sample")
+
+
+# ------------------------------------------------------------------------------------------------
+# recurrent PPO building blocks (stoix/networks/base.py:124-222, stoix/systems/ppo/anakin/rec_ppo.py)
+# ------------------------------------------------------------------------------------------------
+
+
+def gru_workspace(T: int, E: int, H: int, device) -> torch.Tensor:
+    return torch.zeros(int(_lib.load().stx_gru_workspace_bytes(int(T), int(E), int(H))), dtype=torch.uint8, device=device)
+
+
+def gru_sequence_forward(gi: torch.Tensor, reset: torch.Tensor, h0: torch.Tensor, w_h: torch.Tensor, b_hn: torch.Tensor, ws: torch.Tensor,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ScannedRNN(gru) over (T, E): gi (T, E, 3H) input projections, reset (T, E) uint8 / bool, h0 (E, H) -> h_seq (T, E, H)."""
+    dev = _need_cuda(gi, reset, h0, w_h, b_hn, ws, out)
+    T, E, H3 = gi.shape
+    H = H3 // 3
+    r8 = reset.view(torch.uint8) if reset.dtype == torch.bool else reset
+    for t_, shape, name in ((gi, (T, E, 3 * H), "gi"), (h0, (E, H), "h0"), (w_h, (H, 3 * H), "w_h"), (b_hn, (H,), "b_hn")):
+        if t_.dtype != torch.float32 or tuple(t_.shape) != shape or not t_.is_contiguous():
+            raise StxError(f"gru_sequence_forward: {name} must be contiguous float32 {shape}")
+    if r8.dtype != torch.uint8 or tuple(r8.shape) != (T, E) or not r8.is_contiguous():
+        raise StxError("gru_sequence_forward: reset must be contiguous uint8 / bool (T, E)")
+    if out is None:
+        out = torch.empty(T, E, H, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().stx_gru_sequence_forward(_p(gi), _p(r8), _p(h0), _p(w_h), _p(b_hn), T, E, H, _p(out), _p(ws), ws.numel(), _stream()),
+               "stx_gru_sequence_forward")
+    return out
+
+
+def gru_sequence_backward(d_h_seq: torch.Tensor, reset: torch.Tensor, w_h: torch.Tensor, ws: torch.Tensor, d_gi: torch.Tensor,
+                          d_w_h: Optional[torch.Tensor] = None, d_b_hn: Optional[torch.Tensor] = None, grad_weight: float = 1.0,
+                          overwrite: bool = True, d_h0: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(d_h_seq, reset, w_h, ws, d_gi, d_w_h, d_b_hn, d_h0)
+    T, E, H = d_h_seq.shape
+    r8 = reset.view(torch.uint8) if reset.dtype == torch.bool else reset
+    if d_h_seq.dtype != torch.float32 or not d_h_seq.is_contiguous() or d_gi.dtype != torch.float32 or d_gi.numel() != T * E * 3 * H:
+        raise StxError("gru_sequence_backward: d_h_seq (T, E, H) / d_gi (T, E, 3H) must be contiguous float32")
+    _lib.check(_lib.load().stx_gru_sequence_backward(_p(d_h_seq), _p(r8), _p(w_h), T, E, H, _p(ws), ws.numel(), _p(d_gi), _p(d_w_h), _p(d_b_hn),
+                                                     float(grad_weight), int(bool(overwrite)), _p(d_h0), _stream()), "stx_gru_sequence_backward")
+
+
+def ppo_head_grads(logits: Optional[torch.Tensor], value: Optional[torch.Tensor], idx: Optional[torch.Tensor], action, logp_old, v_old, adv, targets,
+                   adv_stats, clip_eps: float, ent_coef: float, vf_coef: float, d_logits, d_value, metrics: torch.Tensor, weight: float = 1.0,
+                   row0: int = 0) -> None:
+    """PPO losses and their gradients w.r.t. network outputs computed elsewhere (see stx_ppo_head_grads)."""
+    dev = _need_cuda(logits, value, idx, action, logp_old, v_old, adv, targets, adv_stats, d_logits, d_value, metrics)
+    mb = int(logits.shape[0]) if logits is not None else int(value.numel())
+    A = int(logits.shape[1]) if logits is not None else 0
+    lib = _lib.load()
+    scratch = _zeros_scratch(("ppo_head",), lib.stx_ppo_head_scratch_bytes(mb), dev)
+    _lib.check(lib.stx_ppo_head_grads(_p(logits), _p(value), _p(idx), int(row0), _p(action), _p(logp_old), _p(v_old), _p(adv), _p(targets), _p(adv_stats),
+                                      mb, A, float(clip_eps), float(ent_coef), float(vf_coef), _p(d_logits), _p(d_value), _p(metrics), float(weight),
+                                      _p(scratch), _stream()), "stx_ppo_head_grads")
