@@ -17,11 +17,14 @@ class Categorical:
 
     def __init__(self, logits: torch.Tensor):
         self.logits = logits
+        self._lead = tuple(logits.shape[:-1])                     # any leading shape, e.g. (T, E) from the recurrent networks
+        self._flat = logits.reshape(-1, logits.shape[-1]).contiguous()
 
     def sample(self, seed=None, offset: int = 0, dev_counter: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`seed` is an int or a PRNG key tensor (any integer tensor: its first two words are used)."""
         s = _seed_to_int(seed)
-        a, lp, _ = ops.categorical(self.logits, None, s, offset, dev_counter)
+        a, lp, _ = ops.categorical(self._flat, None, s, offset, dev_counter)
+        a, lp = a.view(self._lead), lp.view(self._lead)
         self._last = (a, lp)
         return a
 
@@ -29,13 +32,13 @@ class Categorical:
         last = getattr(self, "_last", None)
         if last is not None and last[0] is action:
             return last[1]
-        _, lp, _ = ops.categorical(self.logits, action.to(torch.int32).contiguous())
-        return lp
+        _, lp, _ = ops.categorical(self._flat, action.to(torch.int32).reshape(-1).contiguous())
+        return lp.view(self._lead)
 
     def entropy(self) -> torch.Tensor:
-        a = torch.zeros(self.logits.shape[0], dtype=torch.int32, device=self.logits.device)
-        _, _, ent = ops.categorical(self.logits, a, want_entropy=True)
-        return ent
+        a = torch.zeros(self._flat.shape[0], dtype=torch.int32, device=self.logits.device)
+        _, _, ent = ops.categorical(self._flat, a, want_entropy=True)
+        return ent.view(self._lead)
 
     def mode(self) -> torch.Tensor:
         return torch.argmax(self.logits, dim=-1).to(torch.int32)

@@ -132,6 +132,7 @@ def test_update_steps_match_oracle(chunk):
 
     cfg = _cfg([] if chunk is None else [f"system.recurrent_chunk_size={chunk}"])
     rec_ppo, learn, actor_network, state = _setup(cfg)
+    cfg.arch.num_updates_per_eval = 1     # one update per learn() call; arch.num_updates (3) still drives the LR schedule
     T, E, nmb, epochs = 16, 32, 4, 2
     ch = T if chunk is None else chunk
     nc = T // ch
