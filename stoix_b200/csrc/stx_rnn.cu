@@ -123,6 +123,206 @@ __global__ void gru_dh0_kernel(const float* __restrict__ dhp_gemm, const float* 
   d_h0[i] = reset0[i / H] ? 0.f : dhp_gemm[i] + dhp_direct[i];
 }
 
+
+// ---- persistent sequence kernels -------------------------------------------------------------------------------------------
+// One CTA owns R sequences (rows) for ALL T steps with the whole recurrent matrix W_h (H x 3H fp32, 196 KB at H = 128) resident in
+// shared memory, so the recurrence needs no global synchronisation and no per-step launch: per step the CTA streams gi_t in,
+// does the (R x H) @ (H x 3H) product out of shared memory (thread n owns gate column n for the R rows; W rows are padded to
+// 3H + 1 floats so that both the forward walk (lanes along n) and the transposed walk of the backward (lanes along k) are free
+// of bank conflicts), applies the gates (thread j owns hidden unit j) and writes h_t plus what the backward needs.  The step time
+// is set by reading W_h once from shared memory (3H * H * 4 B / 128 B per clock ~ 1.5k cycles at H = 128), not by launches.
+// Backward: same residency, reverse time; d(gh_t) is kept for the ONE GEMM that forms d(W_h) afterwards.
+template <int R>
+struct GruSmem {
+  __host__ __device__ static size_t w_floats(int H) { return ((size_t)H * (3 * H + 1) + 3) / 4 * 4; }   // keeps the float4 arrays behind it 16-byte aligned
+  static size_t fwd_bytes(int H) { return (w_floats(H) + (size_t)H * R + 2 * (size_t)R * 3 * H) * 4; }
+  static size_t bwd_bytes(int H) { return (w_floats(H) + (size_t)3 * H * R + 3 * (size_t)R * H + (size_t)R * H) * 4; }
+};
+
+__device__ __forceinline__ void gru_load_w(float* __restrict__ Ws, const float* __restrict__ w_h, int H) {
+  const int n3 = 3 * H, total = H * n3;
+  constexpr int U = 8;
+  for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      v[u] = i < total ? __ldg(w_h + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < total) Ws[(i / n3) * (n3 + 1) + i % n3] = v[u];
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024, 1)
+    gru_seq_fwd_kernel(const float* __restrict__ gi, const uint8_t* __restrict__ reset, const float* __restrict__ h0, const float* __restrict__ w_h,
+                       const float* __restrict__ b_hn, int T, int64_t E, int H, float* __restrict__ h_seq, float* __restrict__ hp_seq,
+                       float* __restrict__ rs, float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ ghns) {
+  extern __shared__ __align__(16) float gsm[];
+  const int n3 = 3 * H;
+  float* Ws = gsm;                           // [H][3H + 1]
+  float* hs = Ws + GruSmem<R>::w_floats(H);  // [H][R]   state entering the step, k-major
+  float* ghs = hs + (size_t)H * R;           // [R][3H]
+  float* gis = ghs + (size_t)R * n3;         // [R][3H]
+  const int n = threadIdx.x;                 // gate column (threads >= 3H only help loading)
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  gru_load_w(Ws, w_h, H);
+  for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+    const int j = i / R, r = i % R;
+    const int64_t row = row0 + r;
+    float v = 0.f;
+    if (row < E) {
+      v = reset[row] ? 0.f : h0[row * H + j];
+      hp_seq[row * H + j] = v;
+    }
+    hs[j * R + r] = v;
+  }
+  __syncthreads();
+  const int64_t eh = E * (int64_t)H;
+  for (int t = 0; t < T; ++t) {
+    if (n < n3) {
+      float gir[R], acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r;
+        gir[r] = row < E ? __ldg(gi + ((int64_t)t * E + row) * n3 + n) : 0.f;   // in flight under the product below
+        acc[r] = 0.f;
+      }
+      const float* wcol = Ws + n;
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float w = wcol[(size_t)k * (n3 + 1)];
+        const float* hk = hs + k * R;
+#pragma unroll
+        for (int r4 = 0; r4 < R; r4 += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hk + r4);
+          acc[r4] = fmaf(w, hv.x, acc[r4]), acc[r4 + 1] = fmaf(w, hv.y, acc[r4 + 1]);
+          acc[r4 + 2] = fmaf(w, hv.z, acc[r4 + 2]), acc[r4 + 3] = fmaf(w, hv.w, acc[r4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) ghs[r * n3 + n] = acc[r], gis[r * n3 + n] = gir[r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {   // gates: consecutive threads -> consecutive hidden units of one row
+      const int r = i / H, j = i % H;
+      const int64_t row = row0 + r;
+      if (row >= E) continue;
+      const float* a = gis + r * n3;
+      const float* b = ghs + r * n3;
+      const float rg = sigm(a[j] + b[j]);
+      const float zg = sigm(a[H + j] + b[H + j]);
+      const float ghn = b[2 * H + j] + __ldg(b_hn + j);
+      const float ng = tanhf(a[2 * H + j] + rg * ghn);
+      const float hpv = hs[j * R + r];
+      const float h = (1.f - zg) * ng + zg * hpv;
+      const int64_t o = (int64_t)t * eh + row * H + j;
+      h_seq[o] = h, rs[o] = rg, zs[o] = zg, ns[o] = ng, ghns[o] = ghn;
+      const float hn = (t + 1 < T && reset[(int64_t)(t + 1) * E + row]) ? 0.f : h;
+      hp_seq[o + eh] = hn;
+      hs[j * R + r] = hn;   // only this thread touches (j, r) in this phase; the product above is behind the barrier
+    }
+    __syncthreads();
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024, 1)
+    gru_seq_bwd_kernel(const float* __restrict__ d_h_seq, const uint8_t* __restrict__ reset, const float* __restrict__ w_h, int T, int64_t E, int H,
+                       const float* __restrict__ hp_seq, const float* __restrict__ rs, const float* __restrict__ zs, const float* __restrict__ ns,
+                       const float* __restrict__ ghns, float* __restrict__ d_gi, float* __restrict__ d_gh_seq, float* __restrict__ d_h0) {
+  extern __shared__ __align__(16) float gsm[];
+  const int n3 = 3 * H;
+  float* Ws = gsm;                             // [H][3H + 1]
+  float* dgT = Ws + GruSmem<R>::w_floats(H);   // [3H][R]  d(gh_t), n-major
+  float* part = dgT + (size_t)n3 * R;          // [3][R][H] partial sums of d(gh) W_h^T over the three column blocks
+  float* dh_rec = part + 3 * (size_t)R * H;    // [R][H]   gradient arriving from step t + 1 (already masked by its reset)
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int64_t eh = E * (int64_t)H;
+  gru_load_w(Ws, w_h, H);
+  for (int i = threadIdx.x; i < H * R; i += blockDim.x) dh_rec[i] = 0.f;
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {   // gate gradients
+      const int r = i / H, j = i % H;
+      const int64_t row = row0 + r;
+      float dpr = 0.f, dpz = 0.f, dpn = 0.f, rg = 0.f, direct = 0.f;
+      if (row < E) {
+        const int64_t o = (int64_t)t * eh + row * H + j;
+        const float dh = __ldg(d_h_seq + o) + dh_rec[r * H + j];
+        rg = __ldg(rs + o);
+        const float zg = __ldg(zs + o), ng = __ldg(ns + o), ghn = __ldg(ghns + o), hpv = __ldg(hp_seq + o);
+        const float dn = dh * (1.f - zg), dz = dh * (hpv - ng);
+        dpn = dn * (1.f - ng * ng);
+        dpr = dpn * ghn * rg * (1.f - rg);
+        dpz = dz * zg * (1.f - zg);
+        direct = dh * zg;
+        float* a = d_gi + ((int64_t)t * E + row) * n3;
+        float* b = d_gh_seq + ((int64_t)t * E + row) * n3;
+        a[j] = dpr, a[H + j] = dpz, a[2 * H + j] = dpn;
+        b[j] = dpr, b[H + j] = dpz, b[2 * H + j] = dpn * rg;
+      }
+      dgT[j * R + r] = dpr, dgT[(H + j) * R + r] = dpz, dgT[(2 * H + j) * R + r] = dpn * rg;
+      dh_rec[r * H + j] = direct;   // the direct part of d(hp_t); the W_h^T part is added below
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n3) {     // d(gh_t) W_h^T: thread (k, block) sums the H columns of its block
+      const int k = threadIdx.x % H, blk = threadIdx.x / H;
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      const float* wrow = Ws + (size_t)k * (n3 + 1) + blk * H;
+      const float* dg = dgT + (size_t)blk * H * R;
+#pragma unroll 4
+      for (int nn = 0; nn < H; ++nn) {
+        const float w = wrow[nn];
+#pragma unroll
+        for (int r4 = 0; r4 < R; r4 += 4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dg + nn * R + r4);
+          acc[r4] = fmaf(w, dv.x, acc[r4]), acc[r4 + 1] = fmaf(w, dv.y, acc[r4 + 1]);
+          acc[r4 + 2] = fmaf(w, dv.z, acc[r4 + 2]), acc[r4 + 3] = fmaf(w, dv.w, acc[r4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+      const int r = i / H, j = i % H;
+      const int64_t row = row0 + r;
+      const float dhp = dh_rec[i] + ((part[(size_t)r * H + j] + part[((size_t)R + r) * H + j]) + part[((size_t)2 * R + r) * H + j]);
+      const bool cut = row < E && reset[(int64_t)t * E + row];   // base.py:139-148: the reset cuts the chain into step t - 1
+      dh_rec[i] = (row < E && !cut) ? dhp : 0.f;
+    }
+    __syncthreads();
+  }
+  if (d_h0)
+    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+      const int r = i / H, j = i % H;
+      if (row0 + r < E) d_h0[(row0 + r) * H + j] = dh_rec[i];
+    }
+}
+
+constexpr size_t kGruSmemLimit = 227 * 1024;
+inline bool gru_persistent_ok(int H) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("STX_GRU_PERSISTENT");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return enabled && 3 * H <= 1024 && GruSmem<8>::fwd_bytes(H) <= kGruSmemLimit && GruSmem<8>::bwd_bytes(H) <= kGruSmemLimit;
+}
+template <typename K>
+inline int gru_opt_in(K kernel, size_t bytes) {
+  STX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmemLimit));
+  (void)bytes;
+  return STX_OK;
+}
+
 }  // namespace
 }  // namespace stx
 
@@ -143,6 +343,20 @@ extern "C" int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, c
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
+  if (gru_persistent_ok(H)) {
+    const int threads = ((3 * H + 31) / 32) * 32;
+    if (E >= 1024) {
+      if (int rc = gru_opt_in(gru_seq_fwd_kernel<8>, GruSmem<8>::fwd_bytes(H))) return rc;
+      gru_seq_fwd_kernel<8><<<(unsigned)((E + 7) / 8), threads, GruSmem<8>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq, ws.r, ws.z,
+                                                                                                 ws.n, ws.ghn);
+    } else {
+      if (int rc = gru_opt_in(gru_seq_fwd_kernel<4>, GruSmem<4>::fwd_bytes(H))) return rc;
+      gru_seq_fwd_kernel<4><<<(unsigned)((E + 3) / 4), threads, GruSmem<4>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq, ws.r, ws.z,
+                                                                                                 ws.n, ws.ghn);
+    }
+    STX_LAUNCH_OK();
+    return STX_OK;
+  }
   gru_init_kernel<<<blocks, 256, 0, st>>>(h0, reset, E, H, ws.hp_seq);
   STX_LAUNCH_OK();
   for (int t = 0; t < T; ++t) {
@@ -171,7 +385,21 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  for (int t = T - 1; t >= 0; --t) {
+  const bool persistent = gru_persistent_ok(H);
+  if (persistent) {
+    const int threads = ((3 * H + 31) / 32) * 32;
+    if (E >= 1024) {
+      if (int rc = gru_opt_in(gru_seq_bwd_kernel<8>, GruSmem<8>::bwd_bytes(H))) return rc;
+      gru_seq_bwd_kernel<8><<<(unsigned)((E + 7) / 8), threads, GruSmem<8>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z, ws.n, ws.ghn,
+                                                                                                 d_gi, ws.d_gh_seq, d_h0);
+    } else {
+      if (int rc = gru_opt_in(gru_seq_bwd_kernel<4>, GruSmem<4>::bwd_bytes(H))) return rc;
+      gru_seq_bwd_kernel<4><<<(unsigned)((E + 3) / 4), threads, GruSmem<4>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z, ws.n, ws.ghn,
+                                                                                                 d_gi, ws.d_gh_seq, d_h0);
+    }
+    STX_LAUNCH_OK();
+  }
+  for (int t = T - 1; t >= 0 && !persistent; --t) {
     const bool last = (t == T - 1);
     float* direct = ws.dhp_direct[t & 1];
     gru_gate_bwd_kernel<<<blocks, 256, 0, st>>>(d_h_seq + (size_t)t * eh, last ? nullptr : ws.dhp_gemm, last ? nullptr : ws.dhp_direct[(t + 1) & 1],
@@ -186,7 +414,7 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
       STX_CUDA_OK(simt::launch_gemm<simt::DX>(d, 1, st));
     }
   }
-  if (d_h0) {
+  if (d_h0 && !persistent) {
     gru_dh0_kernel<<<blocks, 256, 0, st>>>(ws.dhp_gemm, ws.dhp_direct[0], reset, E, H, d_h0);
     STX_LAUNCH_OK();
   }

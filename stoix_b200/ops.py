@@ -825,13 +825,13 @@ def gru_sequence_backward(d_h_seq: torch.Tensor, reset: torch.Tensor, w_h: torch
 
 def ppo_head_grads(logits: Optional[torch.Tensor], value: Optional[torch.Tensor], idx: Optional[torch.Tensor], action, logp_old, v_old, adv, targets,
                    adv_stats, clip_eps: float, ent_coef: float, vf_coef: float, d_logits, d_value, metrics: torch.Tensor, weight: float = 1.0,
-                   row0: int = 0) -> None:
+                   row0: int = 0, scratch_key: str = "ppo_head") -> None:
     """PPO losses and their gradients w.r.t. network outputs computed elsewhere (see stx_ppo_head_grads)."""
     dev = _need_cuda(logits, value, idx, action, logp_old, v_old, adv, targets, adv_stats, d_logits, d_value, metrics)
     mb = int(logits.shape[0]) if logits is not None else int(value.numel())
     A = int(logits.shape[1]) if logits is not None else 0
     lib = _lib.load()
-    scratch = _zeros_scratch(("ppo_head",), lib.stx_ppo_head_scratch_bytes(mb), dev)
+    scratch = _zeros_scratch((scratch_key,), lib.stx_ppo_head_scratch_bytes(mb), dev)   # one per concurrently running stream
     _lib.check(lib.stx_ppo_head_grads(_p(logits), _p(value), _p(idx), int(row0), _p(action), _p(logp_old), _p(v_old), _p(adv), _p(targets), _p(adv_stats),
                                       mb, A, float(clip_eps), float(ent_coef), float(vf_coef), _p(d_logits), _p(d_value), _p(metrics), float(weight),
                                       _p(scratch), _stream()), "stx_ppo_head_grads")

@@ -131,6 +131,7 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                      metrics=torch.zeros(epochs, nmb, 8, dtype=torch.float32, device=dev),
                      logits=torch.zeros(E, A, device=dev), reset_mb=torch.zeros(chunk, C, dtype=torch.uint8, device=dev),
                      roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev), perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),
+                     side_stream=torch.cuda.Stream(device=dev), metrics_c=torch.zeros(8, dtype=torch.float32, device=dev),
                      t_rows=(torch.arange(chunk, device=dev, dtype=torch.int64) * cols_total)[:, None])
 
     def _net_step(net, tree, h_cur: torch.Tensor, obs_t: torch.Tensor, reset_t: torch.Tensor):
@@ -146,12 +147,16 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
             sh: _Shard = b["shards"][u]
             for t in range(T):
                 torch.bitwise_or(sh.done[t], sh.trunc[t], out=sh.reset[t])           # reset_hidden_state (:86)
+                main, side = torch.cuda.current_stream(), b["side_stream"]
+                side.wait_stream(main)
+                with torch.cuda.stream(side):      # the critic's step beside the actor's step, sampling and env step
+                    h_c, value = _net_step(critic_net, c_tree, sh.h_c_cur, sh.obs[t], sh.reset[t])
+                    sh.value[t].copy_(value.reshape(-1))
+                    sh.h_critic[t].copy_(h_c), sh.h_c_cur.copy_(h_c)
+                    h_c.record_stream(side), value.record_stream(side)
                 h_a, logits = _net_step(actor_net, a_tree, sh.h_a_cur, sh.obs[t], sh.reset[t])
-                h_c, value = _net_step(critic_net, c_tree, sh.h_c_cur, sh.obs[t], sh.reset[t])
                 ops.categorical(logits.contiguous(), None, state.key[0] + u, t, b["roll_ctr"], out=(sh.action[t], sh.log_prob[t]))
-                sh.value[t].copy_(value.reshape(-1))
-                sh.h_actor[t].copy_(h_a), sh.h_critic[t].copy_(h_c)
-                sh.h_a_cur.copy_(h_a), sh.h_c_cur.copy_(h_c)
+                sh.h_actor[t].copy_(h_a), sh.h_a_cur.copy_(h_a)
                 new_state, ts = env.step(state.env_state[u], sh.action[t])
                 state.env_state[u] = new_state
                 sh.obs[t + 1].copy_(ts.observation)
@@ -161,6 +166,7 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                 em = ts.extras["episode_metrics"]
                 sh.episode_return[t].copy_(em["episode_return"]), sh.episode_length[t].copy_(em["episode_length"])
                 sh.is_terminal_step[t].copy_(em["is_terminal_step"])
+                main.wait_stream(side)             # next step (and the bootstrap value) read h_c_cur / obs written on both streams
             torch.bitwise_or(sh.done[T], sh.trunc[T], out=sh.reset[T])
             _, last_val = _net_step(critic_net, c_tree, sh.h_c_cur, sh.obs[T], sh.reset[T])
             sh.value[T].copy_(torch.where(sh.done[T].bool(), torch.zeros_like(last_val.reshape(-1)), last_val.reshape(-1)))   # :160-163
@@ -191,7 +197,8 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
         stats = sh.adv_stats if sysc.standardize_advantages else None
         ops.ppo_head_grads(w.out if is_actor else None, None if is_actor else w.out, idx, sh.action.reshape(-1), sh.log_prob.reshape(-1),
                            sh.value[:T].reshape(-1), sh.advantages.reshape(-1), sh.targets.reshape(-1), stats, float(sysc.clip_eps), float(sysc.ent_coef),
-                           float(sysc.vf_coef), w.d_out if is_actor else None, None if is_actor else w.d_out, metrics, weight=weight)
+                           float(sysc.vf_coef), w.d_out if is_actor else None, None if is_actor else w.d_out, metrics, weight=weight,
+                           scratch_key="ppo_head_actor" if is_actor else "ppo_head_critic")
         ops.mlp_backward(lay.spec_post, post, w.h_seq.view(chunk * C, H), w.d_out, w.ws_post, net_grad=g_post, grad_weight=weight, overwrite=overwrite,
                          d_input=w.d_h.view(chunk * C, H))
         ops.gru_sequence_backward(w.d_h, b["reset_mb"], w_h, w.ws_gru, w.d_gi, d_w_h=g_wh, d_b_hn=g_bhn, grad_weight=weight, overwrite=overwrite)
@@ -203,8 +210,16 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
         idx = (b["t_rows"] + cols.to(torch.int64)[None, :]).reshape(-1).to(torch.int32)  # row of (t', column j) in the flat (T * E) arrays
         ops.gather_rows(sh.reset[:T].reshape(-1), idx, b["reset_mb"].view(-1))           # done | truncated of the rows (:211, :240)
         a_tree, c_tree = state.params.actor_params, state.params.critic_params
+        # the two networks are independent until the optimiser: the critic's chain of small launches runs on a second stream beside
+        # the actor's (each kernel of the recurrence fills a fraction of the GPU); own metric slots, summed after the join
+        main, side = torch.cuda.current_stream(), b["side_stream"]
+        b["metrics_c"].zero_()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _net_grads(b["lc"], c_tree.flat, b["grads"][b["coff"]:], b["ws_c"], sh, sh.h_critic, idx, False, b["metrics_c"], 1.0 / U, overwrite)
         _net_grads(b["la"], a_tree.flat, b["grads"], b["ws_a"], sh, sh.h_actor, idx, True, metrics, 1.0 / U, overwrite)
-        _net_grads(b["lc"], c_tree.flat, b["grads"][b["coff"]:], b["ws_c"], sh, sh.h_critic, idx, False, metrics, 1.0 / U, overwrite)
+        main.wait_stream(side)
+        metrics.add_(b["metrics_c"])
 
     def _update_phase(state: RNNLearnerState, cols_override: Optional[torch.Tensor] = None) -> None:
         """UPDATE EPOCHS (rec_ppo.py:181-384)."""

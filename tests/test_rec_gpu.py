@@ -21,8 +21,22 @@ dev = lambda x, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(x), devic
 rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("T,E,H", [(7, 33, 20), (1, 64, 128), (16, 300, 128)])
-def test_gru_sequence_matches_oracle(T, E, H):
+@pytest.mark.parametrize("persistent", ["1", "0"])
+@pytest.mark.parametrize("T,E,H", [(7, 33, 20), (1, 64, 128), (16, 300, 128), (5, 1030, 6), (40, 130, 128)])
+def test_gru_sequence_matches_oracle(T, E, H, persistent):
+    """persistent = "1": one CTA per 4 / 8 sequences for all T steps with W_h resident in shared memory (the default);
+    "0": the per-step form (a GEMM + a gate kernel per step), kept as the fallback for hidden sizes whose W_h does not fit."""
+    import subprocess, sys, os
+    if persistent == "0":   # the switch is read once per process: run this case in a child
+        code = ("import os; os.environ['STX_GRU_PERSISTENT']='0'; import sys; sys.path.insert(0, os.getcwd());"
+                f"import tests.test_rec_gpu as m; m._gru_case({T}, {E}, {H}); print('child-ok')")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert "child-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    _gru_case(T, E, H)
+
+
+def _gru_case(T, E, H):
     from stoix_b200 import ops
 
     rng = np.random.default_rng(T * 100 + E)
