@@ -152,11 +152,22 @@ struct SimtPpoWs {
   size_t bytes;
 };
 
-int pick_splits(int64_t mb) {
+// Split-M factor of the weight-gradient GEMMs.  512 rows per split (at most 32) suits wide layers; a network whose thinnest layer
+// has only a few 64x64 output tiles (the 32 -> 128 -> 384 pre-torso of the recurrent nets: 2 tiles) would leave most SMs idle and
+// make every CTA walk thousands of rows, so such networks get as many splits as it takes to fill the GPU twice (>= 256 rows each).
+int pick_splits(const StxMlp* m, int64_t mb) {
   int64_t s = mb / 512;
   if (s < 1) s = 1;
   if (s > 32) s = 32;
-  return (int)s;
+  int64_t min_tiles = 1 << 30;
+  for (int i = 0; i < m->n_layers; ++i) {
+    const int64_t tiles = (int64_t)((m->sizes[i] + 63) / 64) * ((m->sizes[i + 1] + 63) / 64);
+    if (tiles < min_tiles) min_tiles = tiles;
+  }
+  int64_t want = (2 * kNumSMs + min_tiles - 1) / min_tiles;
+  if (want > mb / 256) want = mb / 256;
+  if (want > 128) want = 128;
+  return (int)(s > want ? s : want);
 }
 
 SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
@@ -182,7 +193,7 @@ SimtPpoWs carve(const StxMlp* m, int64_t mb, char* base) {
   w.dhead = reinterpret_cast<float*>(take((size_t)mb * m->sizes[m->n_layers] * 4));
   w.dbuf[0] = reinterpret_cast<float*>(take((size_t)mb * mw * 4));
   w.dbuf[1] = reinterpret_cast<float*>(take((size_t)mb * mw * 4));
-  w.splits = pick_splits(mb);
+  w.splits = pick_splits(m, mb);
   w.partials = reinterpret_cast<float*>(take((size_t)w.splits * stx_mlp_param_count(m) * 4));
   w.loss_partials = reinterpret_cast<double*>(take(((size_t)(mb + 255) / 256) * 6 * 8));
   w.bytes = o;

@@ -34,8 +34,8 @@ struct GruWs {
   size_t bytes;
 };
 
-int gru_splits(int64_t rows) {
-  int64_t s = rows / 4096;
+int gru_splits(int64_t rows) {   // d(W_h) GEMM: (H/64) x (3H/64) output tiles; 512 rows per split fill the GPU from 32k rows on
+  int64_t s = rows / 512;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
   return (int)s;
@@ -132,12 +132,13 @@ __global__ void gru_dh0_kernel(const float* __restrict__ dhp_gemm, const float* 
 // of bank conflicts), applies the gates (thread j owns hidden unit j) and writes h_t plus what the backward needs.  The step time
 // is set by reading W_h once from shared memory (3H * H * 4 B / 128 B per clock ~ 1.5k cycles at H = 128), not by launches.
 // Backward: same residency, reverse time; d(gh_t) is kept for the ONE GEMM that forms d(W_h) afterwards.
-template <int R>
+template <int R, int KS>
 struct GruSmem {
   __host__ __device__ static size_t w_floats(int H) { return ((size_t)H * (3 * H + 1) + 3) / 4 * 4; }   // keeps the float4 arrays behind it 16-byte aligned
-  static size_t fwd_bytes(int H) { return (w_floats(H) + (size_t)H * R + 2 * (size_t)R * 3 * H) * 4; }
-  static size_t bwd_bytes(int H) { return (w_floats(H) + (size_t)3 * H * R + 3 * (size_t)R * H + (size_t)R * H) * 4; }
+  static size_t fwd_bytes(int H) { return (w_floats(H) + (size_t)H * R + (size_t)KS * R * 3 * H) * 4; }
+  static size_t bwd_bytes(int H) { return (w_floats(H) + (size_t)3 * H * R + 3 * (size_t)KS * R * H + (size_t)R * H) * 4; }
 };
+constexpr int kGruItems = 3;   // gate items (row, hidden unit) per thread: H * R <= kGruItems * blockDim for every launch shape
 
 __device__ __forceinline__ void gru_load_w(float* __restrict__ Ws, const float* __restrict__ w_h, int H) {
   const int n3 = 3 * H, total = H * n3;
@@ -157,22 +158,27 @@ __device__ __forceinline__ void gru_load_w(float* __restrict__ Ws, const float* 
   }
 }
 
-template <int R>
+// KS thread groups split the reduction of the per-step product (partials added in a fixed order); what the gate phase of a step
+// needs from global memory (gi_t, reset_{t+1}; backward: the saved gates of step t - 1) is requested BEFORE the product of the
+// step, so its latency hides behind the shared-memory walk instead of sitting in front of the gate arithmetic.
+template <int R, int KS>
 __global__ void __launch_bounds__(1024, 1)
     gru_seq_fwd_kernel(const float* __restrict__ gi, const uint8_t* __restrict__ reset, const float* __restrict__ h0, const float* __restrict__ w_h,
                        const float* __restrict__ b_hn, int T, int64_t E, int H, float* __restrict__ h_seq, float* __restrict__ hp_seq,
                        float* __restrict__ rs, float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ ghns) {
   extern __shared__ __align__(16) float gsm[];
   const int n3 = 3 * H;
-  float* Ws = gsm;                           // [H][3H + 1]
-  float* hs = Ws + GruSmem<R>::w_floats(H);  // [H][R]   state entering the step, k-major
-  float* ghs = hs + (size_t)H * R;           // [R][3H]
-  float* gis = ghs + (size_t)R * n3;         // [R][3H]
-  const int n = threadIdx.x;                 // gate column (threads >= 3H only help loading)
+  float* Ws = gsm;                               // [H][3H + 1]
+  float* hs = Ws + GruSmem<R, KS>::w_floats(H);  // [H][R]   state entering the step, k-major
+  float* ghp = hs + (size_t)H * R;               // [KS][R][3H] partial products
+  const int kh = threadIdx.x / n3, n = threadIdx.x % n3;   // reduction group, gate column
+  const int kper = (H + KS - 1) / KS;
+  const int k_begin = kh * kper, k_end = (k_begin + kper < H) ? k_begin + kper : H;
   const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int items = H * R;
   gru_load_w(Ws, w_h, H);
-  for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
-    const int j = i / R, r = i % R;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int r = i / H, j = i % H;
     const int64_t row = row0 + r;
     float v = 0.f;
     if (row < E) {
@@ -184,17 +190,31 @@ __global__ void __launch_bounds__(1024, 1)
   __syncthreads();
   const int64_t eh = E * (int64_t)H;
   for (int t = 0; t < T; ++t) {
-    if (n < n3) {
-      float gir[R], acc[R];
+    // ---- requests for the gate phase ----
+    float g_r[kGruItems], g_z[kGruItems], g_n[kGruItems], bh[kGruItems];
+    bool cut[kGruItems];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+    for (int q = 0; q < kGruItems; ++q) {
+      const int i = threadIdx.x + q * blockDim.x;
+      g_r[q] = g_z[q] = g_n[q] = bh[q] = 0.f, cut[q] = false;
+      if (i < items) {
+        const int r = i / H, j = i % H;
         const int64_t row = row0 + r;
-        gir[r] = row < E ? __ldg(gi + ((int64_t)t * E + row) * n3 + n) : 0.f;   // in flight under the product below
-        acc[r] = 0.f;
+        if (row < E) {
+          const float* a = gi + ((int64_t)t * E + row) * n3;
+          g_r[q] = __ldg(a + j), g_z[q] = __ldg(a + H + j), g_n[q] = __ldg(a + 2 * H + j), bh[q] = __ldg(b_hn + j);
+          cut[q] = (t + 1 < T) && reset[(int64_t)(t + 1) * E + row] != 0;
+        }
       }
+    }
+    // ---- (R x H) @ (H x 3H), this group's share of k ----
+    if (kh < KS) {
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
       const float* wcol = Ws + n;
 #pragma unroll 4
-      for (int k = 0; k < H; ++k) {
+      for (int k = k_begin; k < k_end; ++k) {
         const float w = wcol[(size_t)k * (n3 + 1)];
         const float* hk = hs + k * R;
 #pragma unroll
@@ -205,24 +225,32 @@ __global__ void __launch_bounds__(1024, 1)
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) ghs[r * n3 + n] = acc[r], gis[r * n3 + n] = gir[r];
+      for (int r = 0; r < R; ++r) ghp[((size_t)kh * R + r) * n3 + n] = acc[r];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {   // gates: consecutive threads -> consecutive hidden units of one row
+    // ---- gates: consecutive threads -> consecutive hidden units of one row ----
+#pragma unroll
+    for (int q = 0; q < kGruItems; ++q) {
+      const int i = threadIdx.x + q * blockDim.x;
+      if (i >= items) continue;
       const int r = i / H, j = i % H;
       const int64_t row = row0 + r;
       if (row >= E) continue;
-      const float* a = gis + r * n3;
-      const float* b = ghs + r * n3;
-      const float rg = sigm(a[j] + b[j]);
-      const float zg = sigm(a[H + j] + b[H + j]);
-      const float ghn = b[2 * H + j] + __ldg(b_hn + j);
-      const float ng = tanhf(a[2 * H + j] + rg * ghn);
+      float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+#pragma unroll
+      for (int g = 0; g < KS; ++g) {   // fixed order over the reduction groups
+        const float* b = ghp + ((size_t)g * R + r) * n3;
+        b_r += b[j], b_z += b[H + j], b_n += b[2 * H + j];
+      }
+      const float rg = sigm(g_r[q] + b_r);
+      const float zg = sigm(g_z[q] + b_z);
+      const float ghn = b_n + bh[q];
+      const float ng = tanhf(g_n[q] + rg * ghn);
       const float hpv = hs[j * R + r];
       const float h = (1.f - zg) * ng + zg * hpv;
       const int64_t o = (int64_t)t * eh + row * H + j;
       h_seq[o] = h, rs[o] = rg, zs[o] = zg, ns[o] = ng, ghns[o] = ghn;
-      const float hn = (t + 1 < T && reset[(int64_t)(t + 1) * E + row]) ? 0.f : h;
+      const float hn = cut[q] ? 0.f : h;
       hp_seq[o + eh] = hn;
       hs[j * R + r] = hn;   // only this thread touches (j, r) in this phase; the product above is behind the barrier
     }
@@ -230,32 +258,60 @@ __global__ void __launch_bounds__(1024, 1)
   }
 }
 
-template <int R>
+template <int R, int KS>
 __global__ void __launch_bounds__(1024, 1)
     gru_seq_bwd_kernel(const float* __restrict__ d_h_seq, const uint8_t* __restrict__ reset, const float* __restrict__ w_h, int T, int64_t E, int H,
                        const float* __restrict__ hp_seq, const float* __restrict__ rs, const float* __restrict__ zs, const float* __restrict__ ns,
                        const float* __restrict__ ghns, float* __restrict__ d_gi, float* __restrict__ d_gh_seq, float* __restrict__ d_h0) {
   extern __shared__ __align__(16) float gsm[];
   const int n3 = 3 * H;
-  float* Ws = gsm;                             // [H][3H + 1]
-  float* dgT = Ws + GruSmem<R>::w_floats(H);   // [3H][R]  d(gh_t), n-major
-  float* part = dgT + (size_t)n3 * R;          // [3][R][H] partial sums of d(gh) W_h^T over the three column blocks
-  float* dh_rec = part + 3 * (size_t)R * H;    // [R][H]   gradient arriving from step t + 1 (already masked by its reset)
+  constexpr int NB = 3 * KS;                       // column blocks of the transposed product
+  float* Ws = gsm;                                 // [H][3H + 1]
+  float* dgT = Ws + GruSmem<R, KS>::w_floats(H);   // [3H][R]  d(gh_t), n-major
+  float* part = dgT + (size_t)n3 * R;              // [NB][R][H] partial sums of d(gh) W_h^T over the column blocks
+  float* dh_rec = part + (size_t)NB * R * H;       // [R][H]   gradient arriving from step t + 1 (already masked by its reset)
   const int64_t row0 = (int64_t)blockIdx.x * R;
   const int64_t eh = E * (int64_t)H;
+  const int items = H * R;
   gru_load_w(Ws, w_h, H);
-  for (int i = threadIdx.x; i < H * R; i += blockDim.x) dh_rec[i] = 0.f;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) dh_rec[i] = 0.f;
+  // saved values of the step the gate phase will process next (requested one step ahead)
+  float v_dh[kGruItems], v_r[kGruItems], v_z[kGruItems], v_n[kGruItems], v_g[kGruItems], v_hp[kGruItems];
+  bool v_cut[kGruItems];
+  auto request = [&](int t) {
+#pragma unroll
+    for (int q = 0; q < kGruItems; ++q) {
+      const int i = threadIdx.x + q * blockDim.x;
+      v_dh[q] = v_r[q] = v_z[q] = v_n[q] = v_g[q] = v_hp[q] = 0.f, v_cut[q] = false;
+      if (i < items && t >= 0) {
+        const int r = i / H, j = i % H;
+        const int64_t row = row0 + r;
+        if (row < E) {
+          const int64_t o = (int64_t)t * eh + row * H + j;
+          v_dh[q] = __ldg(d_h_seq + o), v_r[q] = __ldg(rs + o), v_z[q] = __ldg(zs + o), v_n[q] = __ldg(ns + o), v_g[q] = __ldg(ghns + o);
+          v_hp[q] = __ldg(hp_seq + o);
+          v_cut[q] = reset[(int64_t)t * E + row] != 0;
+        }
+      }
+    }
+  };
+  request(T - 1);
   __syncthreads();
+  const int kcol = (H + KS - 1) / KS;               // columns per block of the transposed product
   for (int t = T - 1; t >= 0; --t) {
-    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {   // gate gradients
+    bool cut_t[kGruItems];
+#pragma unroll
+    for (int q = 0; q < kGruItems; ++q) {            // gate gradients of step t from the values requested earlier
+      const int i = threadIdx.x + q * blockDim.x;
+      cut_t[q] = v_cut[q];
+      if (i >= items) continue;
       const int r = i / H, j = i % H;
       const int64_t row = row0 + r;
       float dpr = 0.f, dpz = 0.f, dpn = 0.f, rg = 0.f, direct = 0.f;
       if (row < E) {
-        const int64_t o = (int64_t)t * eh + row * H + j;
-        const float dh = __ldg(d_h_seq + o) + dh_rec[r * H + j];
-        rg = __ldg(rs + o);
-        const float zg = __ldg(zs + o), ng = __ldg(ns + o), ghn = __ldg(ghns + o), hpv = __ldg(hp_seq + o);
+        const float dh = v_dh[q] + dh_rec[r * H + j];
+        rg = v_r[q];
+        const float zg = v_z[q], ng = v_n[q], ghn = v_g[q], hpv = v_hp[q];
         const float dn = dh * (1.f - zg), dz = dh * (hpv - ng);
         dpn = dn * (1.f - ng * ng);
         dpr = dpn * ghn * rg * (1.f - rg);
@@ -269,20 +325,22 @@ __global__ void __launch_bounds__(1024, 1)
       dgT[j * R + r] = dpr, dgT[(H + j) * R + r] = dpz, dgT[(2 * H + j) * R + r] = dpn * rg;
       dh_rec[r * H + j] = direct;   // the direct part of d(hp_t); the W_h^T part is added below
     }
+    request(t - 1);                 // in flight under the product
     __syncthreads();
-    if ((int)threadIdx.x < n3) {     // d(gh_t) W_h^T: thread (k, block) sums the H columns of its block
+    if ((int)threadIdx.x < NB * H) {   // d(gh_t) W_h^T: thread (k, block) sums the columns of its block
       const int k = threadIdx.x % H, blk = threadIdx.x / H;
+      const int gate = blk / KS, sub = blk % KS;                 // block = (gate, sub-range of its H columns)
+      const int c0 = gate * H + sub * kcol, c1 = (sub * kcol + kcol < H) ? c0 + kcol : gate * H + H;
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.f;
-      const float* wrow = Ws + (size_t)k * (n3 + 1) + blk * H;
-      const float* dg = dgT + (size_t)blk * H * R;
+      const float* wrow = Ws + (size_t)k * (n3 + 1);
 #pragma unroll 4
-      for (int nn = 0; nn < H; ++nn) {
+      for (int nn = c0; nn < c1; ++nn) {
         const float w = wrow[nn];
 #pragma unroll
         for (int r4 = 0; r4 < R; r4 += 4) {
-          const float4 dv = *reinterpret_cast<const float4*>(dg + nn * R + r4);
+          const float4 dv = *reinterpret_cast<const float4*>(dgT + (size_t)nn * R + r4);
           acc[r4] = fmaf(w, dv.x, acc[r4]), acc[r4 + 1] = fmaf(w, dv.y, acc[r4 + 1]);
           acc[r4 + 2] = fmaf(w, dv.z, acc[r4 + 2]), acc[r4 + 3] = fmaf(w, dv.w, acc[r4 + 3]);
         }
@@ -291,35 +349,41 @@ __global__ void __launch_bounds__(1024, 1)
       for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < kGruItems; ++q) {
+      const int i = threadIdx.x + q * blockDim.x;
+      if (i >= items) continue;
       const int r = i / H, j = i % H;
       const int64_t row = row0 + r;
-      const float dhp = dh_rec[i] + ((part[(size_t)r * H + j] + part[((size_t)R + r) * H + j]) + part[((size_t)2 * R + r) * H + j]);
-      const bool cut = row < E && reset[(int64_t)t * E + row];   // base.py:139-148: the reset cuts the chain into step t - 1
-      dh_rec[i] = (row < E && !cut) ? dhp : 0.f;
+      float dhp = dh_rec[i];
+#pragma unroll
+      for (int blk = 0; blk < NB; ++blk) dhp += part[((size_t)blk * R + r) * H + j];   // fixed order
+      dh_rec[i] = (row < E && !cut_t[q]) ? dhp : 0.f;   // base.py:139-148: the reset of step t cuts the chain into step t - 1
     }
     __syncthreads();
   }
   if (d_h0)
-    for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
       const int r = i / H, j = i % H;
       if (row0 + r < E) d_h0[(row0 + r) * H + j] = dh_rec[i];
     }
 }
 
 constexpr size_t kGruSmemLimit = 227 * 1024;
+// launch shape: R = 8 rows per CTA from 1024 sequences up (the rollout step), else 4 with the reduction split over two thread groups
+inline int gru_threads(int H, int ks) { return ((ks * 3 * H + 31) / 32) * 32; }
 inline bool gru_persistent_ok(int H) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("STX_GRU_PERSISTENT");
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  return enabled && 3 * H <= 1024 && GruSmem<8>::fwd_bytes(H) <= kGruSmemLimit && GruSmem<8>::bwd_bytes(H) <= kGruSmemLimit;
+  return enabled && H >= 2 && gru_threads(H, 2) <= 1024 && GruSmem<8, 1>::fwd_bytes(H) <= kGruSmemLimit && GruSmem<8, 1>::bwd_bytes(H) <= kGruSmemLimit &&
+         GruSmem<4, 2>::fwd_bytes(H) <= kGruSmemLimit && GruSmem<4, 2>::bwd_bytes(H) <= kGruSmemLimit;
 }
 template <typename K>
-inline int gru_opt_in(K kernel, size_t bytes) {
+inline int gru_opt_in(K kernel) {
   STX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmemLimit));
-  (void)bytes;
   return STX_OK;
 }
 
@@ -344,15 +408,14 @@ extern "C" int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, c
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
   if (gru_persistent_ok(H)) {
-    const int threads = ((3 * H + 31) / 32) * 32;
     if (E >= 1024) {
-      if (int rc = gru_opt_in(gru_seq_fwd_kernel<8>, GruSmem<8>::fwd_bytes(H))) return rc;
-      gru_seq_fwd_kernel<8><<<(unsigned)((E + 7) / 8), threads, GruSmem<8>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq, ws.r, ws.z,
-                                                                                                 ws.n, ws.ghn);
+      if (int rc = gru_opt_in(gru_seq_fwd_kernel<8, 1>)) return rc;
+      gru_seq_fwd_kernel<8, 1><<<(unsigned)((E + 7) / 8), gru_threads(H, 1), GruSmem<8, 1>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq,
+                                                                                                                  ws.r, ws.z, ws.n, ws.ghn);
     } else {
-      if (int rc = gru_opt_in(gru_seq_fwd_kernel<4>, GruSmem<4>::fwd_bytes(H))) return rc;
-      gru_seq_fwd_kernel<4><<<(unsigned)((E + 3) / 4), threads, GruSmem<4>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq, ws.r, ws.z,
-                                                                                                 ws.n, ws.ghn);
+      if (int rc = gru_opt_in(gru_seq_fwd_kernel<4, 2>)) return rc;
+      gru_seq_fwd_kernel<4, 2><<<(unsigned)((E + 3) / 4), gru_threads(H, 2), GruSmem<4, 2>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq,
+                                                                                                                  ws.r, ws.z, ws.n, ws.ghn);
     }
     STX_LAUNCH_OK();
     return STX_OK;
@@ -387,15 +450,14 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
   const unsigned blocks = (unsigned)((eh + 255) / 256);
   const bool persistent = gru_persistent_ok(H);
   if (persistent) {
-    const int threads = ((3 * H + 31) / 32) * 32;
     if (E >= 1024) {
-      if (int rc = gru_opt_in(gru_seq_bwd_kernel<8>, GruSmem<8>::bwd_bytes(H))) return rc;
-      gru_seq_bwd_kernel<8><<<(unsigned)((E + 7) / 8), threads, GruSmem<8>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z, ws.n, ws.ghn,
-                                                                                                 d_gi, ws.d_gh_seq, d_h0);
+      if (int rc = gru_opt_in(gru_seq_bwd_kernel<8, 1>)) return rc;
+      gru_seq_bwd_kernel<8, 1><<<(unsigned)((E + 7) / 8), gru_threads(H, 1), GruSmem<8, 1>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z,
+                                                                                                                  ws.n, ws.ghn, d_gi, ws.d_gh_seq, d_h0);
     } else {
-      if (int rc = gru_opt_in(gru_seq_bwd_kernel<4>, GruSmem<4>::bwd_bytes(H))) return rc;
-      gru_seq_bwd_kernel<4><<<(unsigned)((E + 3) / 4), threads, GruSmem<4>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z, ws.n, ws.ghn,
-                                                                                                 d_gi, ws.d_gh_seq, d_h0);
+      if (int rc = gru_opt_in(gru_seq_bwd_kernel<4, 2>)) return rc;
+      gru_seq_bwd_kernel<4, 2><<<(unsigned)((E + 3) / 4), gru_threads(H, 2), GruSmem<4, 2>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z,
+                                                                                                                  ws.n, ws.ghn, d_gi, ws.d_gh_seq, d_h0);
     }
     STX_LAUNCH_OK();
   }

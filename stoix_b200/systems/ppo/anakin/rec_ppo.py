@@ -19,6 +19,7 @@ discount_t = (1 - last_done_t) * gamma; minibatches are column subsets of the ba
 from __future__ import annotations
 
 import copy
+import gc
 import os
 import sys
 import time
@@ -32,7 +33,7 @@ from stoix_b200 import optim as optax
 from stoix_b200 import random as srandom
 from stoix_b200.base_types import ActorCriticOptStates, ActorCriticParams, AnakinExperimentOutput
 from stoix_b200.config import DictConfig, compose, instantiate, to_container
-from stoix_b200.envs.base import Environment, TimeStep
+from stoix_b200.envs.base import Environment, StepOut, TimeStep
 from stoix_b200.networks.recurrent import RecLayout, RecurrentActor, RecurrentCritic, ScannedRNN
 from stoix_b200.systems.ppo.ppo_types import ActorCriticHiddenStates, RNNLearnerState, RNNPPOTransition
 from stoix_b200.utils import make_env as environments
@@ -66,6 +67,7 @@ class _Shard:
         self.advantages, self.targets, self.adv_stats = z(T, E), z(T, E), z(2)
         self.episode_return, self.episode_length = z(T, E), z(T, E, dt=torch.int32)
         self.is_terminal_step = z(T, E, dt=torch.bool)
+        self.next_obs_scratch = z(E, D)                 # extras["next_obs"] is not used by rec_ppo
 
     def transition(self, T: int) -> RNNPPOTransition:
         return RNNPPOTransition(self.done[:T], self.trunc[:T], self.action, self.value[:T], self.reward, self.log_prob, self.obs[:T],
@@ -111,6 +113,8 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
     assert cols_total % nmb == 0, "num_envs * num_recurrent_chunks must be divisible by num_minibatches"
     C = cols_total // nmb
     gamma, lam = float(sysc.gamma), float(sysc.gae_lambda)
+    use_graph = bool(arch.get("cuda_graph", True))
+    has_step_into = hasattr(env, "step_into")
     built: Dict[str, Any] = {}
 
     def _build(state: RNNLearnerState) -> None:
@@ -132,6 +136,7 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                      logits=torch.zeros(E, A, device=dev), reset_mb=torch.zeros(chunk, C, dtype=torch.uint8, device=dev),
                      roll_ctr=torch.zeros(1, dtype=torch.int64, device=dev), perm_ctr=torch.zeros(1, dtype=torch.int64, device=dev),
                      side_stream=torch.cuda.Stream(device=dev), metrics_c=torch.zeros(8, dtype=torch.float32, device=dev),
+                     graph=None, eager_done=False,
                      t_rows=(torch.arange(chunk, device=dev, dtype=torch.int64) * cols_total)[:, None])
 
     def _net_step(net, tree, h_cur: torch.Tensor, obs_t: torch.Tensor, reset_t: torch.Tensor):
@@ -157,19 +162,26 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                 h_a, logits = _net_step(actor_net, a_tree, sh.h_a_cur, sh.obs[t], sh.reset[t])
                 ops.categorical(logits.contiguous(), None, state.key[0] + u, t, b["roll_ctr"], out=(sh.action[t], sh.log_prob[t]))
                 sh.h_actor[t].copy_(h_a), sh.h_a_cur.copy_(h_a)
-                new_state, ts = env.step(state.env_state[u], sh.action[t])
-                state.env_state[u] = new_state
-                sh.obs[t + 1].copy_(ts.observation)
-                sh.reward[t].copy_(ts.reward)
-                sh.done[t + 1].copy_(ts.discount == 0.0)                              # :105
-                sh.trunc[t + 1].copy_(ts.last() & (ts.discount != 0.0))               # :106
-                em = ts.extras["episode_metrics"]
-                sh.episode_return[t].copy_(em["episode_return"]), sh.episode_length[t].copy_(em["episode_length"])
-                sh.is_terminal_step[t].copy_(em["is_terminal_step"])
+                if has_step_into:   # zero-copy: the env kernel writes the transition rows in place (device-resident step counter)
+                    env.step_into(state.env_state[u], sh.action[t],
+                                  StepOut(sh.obs[t + 1], sh.next_obs_scratch, sh.reward[t], sh.done[t + 1], sh.trunc[t + 1], sh.episode_return[t],
+                                          sh.episode_length[t], sh.is_terminal_step[t].view(torch.uint8)), t)
+                else:
+                    new_state, ts = env.step(state.env_state[u], sh.action[t])
+                    state.env_state[u] = new_state
+                    sh.obs[t + 1].copy_(ts.observation)
+                    sh.reward[t].copy_(ts.reward)
+                    sh.done[t + 1].copy_(ts.discount == 0.0)                              # :105
+                    sh.trunc[t + 1].copy_(ts.last() & (ts.discount != 0.0))               # :106
+                    em = ts.extras["episode_metrics"]
+                    sh.episode_return[t].copy_(em["episode_return"]), sh.episode_length[t].copy_(em["episode_length"])
+                    sh.is_terminal_step[t].copy_(em["is_terminal_step"])
                 main.wait_stream(side)             # next step (and the bootstrap value) read h_c_cur / obs written on both streams
             torch.bitwise_or(sh.done[T], sh.trunc[T], out=sh.reset[T])
             _, last_val = _net_step(critic_net, c_tree, sh.h_c_cur, sh.obs[T], sh.reset[T])
             sh.value[T].copy_(torch.where(sh.done[T].bool(), torch.zeros_like(last_val.reshape(-1)), last_val.reshape(-1)))   # :160-163
+            if has_step_into and hasattr(env, "advance"):
+                env.advance(state.env_state[u], T)
         ops.counter_add(b["roll_ctr"], T)
 
     def _gae_phase(state: RNNLearnerState) -> None:
@@ -257,7 +269,24 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                   "is_terminal_step": torch.empty(n_upd, U, T, E, dtype=torch.bool, device=dev)}
         train_out = torch.empty(n_upd, epochs, nmb, 8, device=dev)
         for k in range(n_upd):
-            _update_step(learner_state)
+            if use_graph and b["eager_done"] and b["graph"] is None:   # one CUDA graph per update step, as ff_ppo: ~10k launches replayed
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                gc.collect()
+                gc_was_enabled = gc.isenabled()
+                gc.disable()
+                try:
+                    with torch.cuda.graph(g):
+                        _update_step(learner_state)
+                finally:
+                    if gc_was_enabled:
+                        gc.enable()
+                b["graph"] = g
+            if b["graph"] is not None:
+                b["graph"].replay()
+            else:
+                _update_step(learner_state)
+                b["eager_done"] = True
             for u in range(U):
                 sh = b["shards"][u]
                 ep_out["episode_return"][k, u].copy_(sh.episode_return), ep_out["episode_length"][k, u].copy_(sh.episode_length)
