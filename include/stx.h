@@ -431,6 +431,14 @@ int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, const float*
 int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* reset, const float* w_h, int T, int64_t E, int H, void* workspace,
                               size_t workspace_bytes, float* d_gi, float* d_w_h, float* d_b_hn, float grad_weight, int overwrite, float* d_h0,
                               void* stream);
+/* LSTM form of the above: ScannedRNN(cell_type="lstm") (flax.linen.LSTMCell: i, f, g, o gates; c' = f c + i g, h' = o tanh(c')).
+ *   gi [T][E][4H] (columns i | f | g | o; the four hidden biases ride on the input projection), carry [E][2H] = (c | h), both halves
+ *   zeroed at a reset, w_h [H][4H]; carry_last (nullable) = the carry after step T-1.  Per-step launches (W_h does not fit one SM). */
+size_t stx_lstm_workspace_bytes(int T, int64_t E, int H);
+int stx_lstm_sequence_forward(const float* gi, const uint8_t* reset, const float* carry0, const float* w_h, int T, int64_t E, int H, float* h_seq,
+                              float* carry_last, void* workspace, size_t workspace_bytes, void* stream);
+int stx_lstm_sequence_backward(const float* d_h_seq, const uint8_t* reset, const float* w_h, int T, int64_t E, int H, void* workspace,
+                               size_t workspace_bytes, float* d_gi, float* d_w_h, float grad_weight, int overwrite, float* d_carry0, void* stream);
 size_t stx_ppo_head_scratch_bytes(int64_t mb);
 int stx_ppo_head_grads(const float* logits, const float* value, const int32_t* idx, int64_t row0, const int32_t* action, const float* logp_old,
                        const float* v_old, const float* adv, const float* targets, const float* adv_stats, int64_t mb, int A, float clip_eps,

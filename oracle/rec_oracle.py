@@ -45,6 +45,10 @@ class RecNet:
     def H(self) -> int:
         return self.Wh.shape[0]
 
+    @property
+    def is_lstm(self) -> bool:   # W_h (H, 4H), no separate b_hn (empty): the four hidden biases are the bias of the input projection
+        return self.Wh.shape[1] == 4 * self.Wh.shape[0]
+
     def flat(self) -> np.ndarray:
         return np.concatenate([self.pre.flat(), self.Wh.ravel(), self.bhn.ravel(), self.post.flat()])
 
@@ -53,10 +57,12 @@ class RecNet:
         n_pre = sum(pre_sizes[i] * pre_sizes[i + 1] + pre_sizes[i + 1] for i in range(len(pre_sizes) - 1))
         o = n_pre
         pre = O.MLPParams.from_flat(flat[:o], list(pre_sizes), activation)
-        Wh = flat[o:o + H * 3 * H].reshape(H, 3 * H).copy()
-        o += H * 3 * H
-        bhn = flat[o:o + H].copy()
-        o += H
+        G = pre_sizes[-1] // H          # 3 gate blocks: GRU (followed by b_hn), 4: LSTM (no extra bias)
+        Wh = flat[o:o + H * G * H].reshape(H, G * H).copy()
+        o += H * G * H
+        nb = H if G == 3 else 0
+        bhn = flat[o:o + nb].copy()
+        o += nb
         post = O.MLPParams.from_flat(flat[o:], list(post_sizes), activation)
         return RecNet(pre, Wh, bhn, post)
 
@@ -103,13 +109,61 @@ def gru_backward(cache, reset: np.ndarray, d_hseq: np.ndarray, Wh: np.ndarray):
     return d_gi, dWh, dbhn, dh_rec
 
 
+def lstm_forward(gi: np.ndarray, reset: np.ndarray, carry0: np.ndarray, Wh: np.ndarray):
+    """ScannedRNN(cell_type="lstm") over T steps.  flax.linen.LSTMCell (published definition; the hidden Denses carry the biases):
+        i = sigmoid(W_ii x + W_hi h + b_hi)   f = sigmoid(W_if x + W_hf h + b_hf)   g = tanh(W_ig x + W_hg h + b_hg)
+        o = sigmoid(W_io x + W_ho h + b_ho)   c' = f c + i g   h' = o tanh(c')      carry = (c', h'), output = h'
+    gi (T, E, 4H) = W_i x + b_h (columns i|f|g|o: the four hidden biases ride on the input projection, the sum is the same),
+    carry0 (E, 2H) = (c | h), Wh (H, 4H).  Both halves of the carry are zeroed where reset_t is set (base.py:139-148 tree_map)."""
+    T, E, H4 = gi.shape
+    H = H4 // 4
+    c, h = carry0[:, :H], carry0[:, H:]
+    hs, cs, cache = [], [], []
+    for t in range(T):
+        cp = np.where(reset[t][:, None], 0.0, c)
+        hp = np.where(reset[t][:, None], 0.0, h)
+        z = gi[t] + hp @ Wh
+        i, f, g, o = _sigmoid(z[:, :H]), _sigmoid(z[:, H:2 * H]), np.tanh(z[:, 2 * H:3 * H]), _sigmoid(z[:, 3 * H:])
+        c = f * cp + i * g
+        tc = np.tanh(c)
+        h = o * tc
+        hs.append(h), cs.append(c)
+        cache.append((cp, hp, i, f, g, o, tc))
+    return np.stack(hs), np.concatenate([c, h], 1), cache
+
+
+def lstm_backward(cache, reset: np.ndarray, d_hseq: np.ndarray, Wh: np.ndarray):
+    """Reverse-mode of lstm_forward: d(gi), d(Wh), d(carry0) given d(loss)/d(h_t) for every t."""
+    T, E, H = d_hseq.shape
+    d_gi = np.zeros((T, E, 4 * H), d_hseq.dtype)
+    dWh = np.zeros_like(Wh)
+    dh_rec, dc_rec = np.zeros((E, H), d_hseq.dtype), np.zeros((E, H), d_hseq.dtype)
+    for t in range(T - 1, -1, -1):
+        cp, hp, i, f, g, o, tc = cache[t]
+        dh = d_hseq[t] + dh_rec
+        do = dh * tc
+        dc = dc_rec + dh * o * (1.0 - tc * tc)
+        di, df, dg, dcp = dc * g, dc * cp, dc * i, dc * f
+        dz = np.concatenate([di * i * (1 - i), df * f * (1 - f), dg * (1 - g * g), do * o * (1 - o)], axis=1)
+        d_gi[t] = dz
+        dWh += hp.T @ dz
+        dhp = dz @ Wh.T
+        dh_rec = np.where(reset[t][:, None], 0.0, dhp)
+        dc_rec = np.where(reset[t][:, None], 0.0, dcp)
+    return d_gi, dWh, np.concatenate([dc_rec, dh_rec], 1)
+
+
 def rec_forward(net: RecNet, h0: np.ndarray, obs: np.ndarray, reset: np.ndarray):
     """RecurrentActor / RecurrentCritic.__call__ (networks/base.py:162-222): obs (T, E, D) -> out (T, E, A), last hidden state."""
     T, E, D = obs.shape
     gi, c_pre = O.mlp_forward(net.pre, obs.reshape(T * E, D))
-    h_seq, c_gru = gru_forward(gi.reshape(T, E, -1), reset, h0, net.Wh, net.bhn)
+    if net.is_lstm:   # carry = (c | h), (E, 2H)
+        h_seq, last, c_gru = lstm_forward(gi.reshape(T, E, -1), reset, h0, net.Wh)
+    else:
+        h_seq, c_gru = gru_forward(gi.reshape(T, E, -1), reset, h0, net.Wh, net.bhn)
+        last = h_seq[-1]
     out, c_post = O.mlp_forward(net.post, h_seq.reshape(T * E, -1))
-    return out.reshape(T, E, -1), h_seq[-1], (c_pre, c_gru, c_post, h_seq, reset)
+    return out.reshape(T, E, -1), last, (c_pre, c_gru, c_post, h_seq, reset)
 
 
 def rec_backward(net: RecNet, cache, d_out: np.ndarray) -> RecNet:
@@ -118,7 +172,11 @@ def rec_backward(net: RecNet, cache, d_out: np.ndarray) -> RecNet:
     d2 = d_out.reshape(T * E, -1)
     g_post = O.mlp_backward(net.post, c_post, d2)
     d_h = mlp_input_grad(net.post, c_post, d2).reshape(T, E, H)
-    d_gi, dWh, dbhn, _ = gru_backward(c_gru, reset, d_h, net.Wh)
+    if net.is_lstm:
+        d_gi, dWh, _ = lstm_backward(c_gru, reset, d_h, net.Wh)
+        dbhn = np.zeros_like(net.bhn)
+    else:
+        d_gi, dWh, dbhn, _ = gru_backward(c_gru, reset, d_h, net.Wh)
     g_pre = O.mlp_backward(net.pre, c_pre, d_gi.reshape(T * E, -1))
     return RecNet(g_pre, dWh, dbhn, g_post)
 

@@ -162,6 +162,9 @@ _SIGNATURES = {
     "stx_gru_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int]),
     "stx_gru_sequence_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P]),
     "stx_gru_sequence_backward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_float, C.c_int, _P, _P]),
+    "stx_lstm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int]),
+    "stx_lstm_sequence_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "stx_lstm_sequence_backward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_size_t, _P, _P, C.c_float, C.c_int, _P, _P]),
     "stx_ppo_head_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "stx_ppo_head_grads": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P,
                                      C.c_float, _P, _P]),

@@ -369,6 +369,105 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
+// ---- LSTM (flax.linen.LSTMCell), per-step form ----------------------------------------------------------------------------
+// i = sigmoid(z_i), f = sigmoid(z_f), g = tanh(z_g), o = sigmoid(z_o) with z = gi_t + hp W_h (gi carries the four hidden biases);
+// c' = f cp + i g, h' = o tanh(c'); carry = (c | h), both halves zeroed at a reset.  W_h (H x 4H fp32) is 262 KB at H = 128 and
+// does not fit one SM's shared memory, so this cell runs as one small-grid GEMM + one gate kernel per step (a 2-CTA cluster
+// holding half of the hidden units each is the persistent form it would need).  d(gi_t) = d(gh_t) = d(z_t): one buffer.
+struct LstmWs {
+  float *hp_seq, *cp_seq;          // [T + 1][E][H]  h / c entering step t (after the reset)
+  float *gi_, *gf_, *gg_, *go_, *tc_;  // [T][E][H]
+  float *gh;                       // [E][4H]
+  float *dhp_gemm;                 // [E][H]
+  float *dcp[2];                   // [E][H]
+  float *partials;                 // [splits][H * 4H]
+  int splits;
+  size_t bytes;
+};
+LstmWs carve_lstm(int T, int64_t E, int H, char* base) {
+  LstmWs w{};
+  size_t o = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(base + o) : nullptr;
+    o += ralign(floats * 4);
+    return p;
+  };
+  const size_t eh = (size_t)E * H;
+  w.hp_seq = take((size_t)(T + 1) * eh), w.cp_seq = take((size_t)(T + 1) * eh);
+  w.gi_ = take((size_t)T * eh), w.gf_ = take((size_t)T * eh), w.gg_ = take((size_t)T * eh), w.go_ = take((size_t)T * eh), w.tc_ = take((size_t)T * eh);
+  w.gh = take(4 * eh);
+  w.dhp_gemm = take(eh);
+  w.dcp[0] = take(eh), w.dcp[1] = take(eh);
+  w.splits = gru_splits((int64_t)T * E);
+  w.partials = take((size_t)w.splits * (size_t)H * 4 * H);
+  w.bytes = o;
+  return w;
+}
+
+__global__ void lstm_init_kernel(const float* __restrict__ carry0, const uint8_t* __restrict__ reset0, int64_t E, int H, float* __restrict__ cp0,
+                                 float* __restrict__ hp0) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= E * H) return;
+  const int64_t e = i / H;
+  const int k = (int)(i % H);
+  const bool cut = reset0[e] != 0;
+  cp0[i] = cut ? 0.f : carry0[e * 2 * H + k];
+  hp0[i] = cut ? 0.f : carry0[e * 2 * H + H + k];
+}
+
+__global__ void lstm_gate_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ cp,
+                                     const uint8_t* __restrict__ reset_next, int64_t E, int H, float* __restrict__ h_out, float* __restrict__ cp_next,
+                                     float* __restrict__ hp_next, float* __restrict__ si, float* __restrict__ sf, float* __restrict__ sg,
+                                     float* __restrict__ so, float* __restrict__ stc, float* __restrict__ carry_last) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= E * H) return;
+  const int64_t e = idx / H;
+  const int k = (int)(idx % H);
+  const float* a = gi + e * 4 * H;
+  const float* b = gh + e * 4 * H;
+  const float ig = sigm(a[k] + b[k]), fg = sigm(a[H + k] + b[H + k]), gg = tanhf(a[2 * H + k] + b[2 * H + k]), og = sigm(a[3 * H + k] + b[3 * H + k]);
+  const float c = fg * cp[idx] + ig * gg;
+  const float tc = tanhf(c);
+  const float h = og * tc;
+  h_out[idx] = h;
+  si[idx] = ig, sf[idx] = fg, sg[idx] = gg, so[idx] = og, stc[idx] = tc;
+  const bool cut = reset_next && reset_next[e];
+  cp_next[idx] = cut ? 0.f : c;
+  hp_next[idx] = cut ? 0.f : h;
+  if (carry_last) carry_last[e * 2 * H + k] = c, carry_last[e * 2 * H + H + k] = h;
+}
+
+__global__ void lstm_gate_bwd_kernel(const float* __restrict__ d_h_out, const float* __restrict__ dhp_gemm_next, const float* __restrict__ dcp_next,
+                                     const uint8_t* __restrict__ reset_next, const float* __restrict__ si, const float* __restrict__ sf,
+                                     const float* __restrict__ sg, const float* __restrict__ so, const float* __restrict__ stc,
+                                     const float* __restrict__ cp, int64_t E, int H, float* __restrict__ d_z, float* __restrict__ dcp_out) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= E * H) return;
+  const int64_t e = idx / H;
+  const int k = (int)(idx % H);
+  float dh = d_h_out[idx], dc = 0.f;
+  if (dhp_gemm_next && !reset_next[e]) dh += dhp_gemm_next[idx], dc = dcp_next[idx];   // the reset cuts both halves of the carry
+  const float ig = si[idx], fg = sf[idx], gg = sg[idx], og = so[idx], tc = stc[idx];
+  dc += dh * og * (1.f - tc * tc);
+  float* z = d_z + e * 4 * H;
+  z[k] = dc * gg * ig * (1.f - ig);
+  z[H + k] = dc * cp[idx] * fg * (1.f - fg);
+  z[2 * H + k] = dc * ig * (1.f - gg * gg);
+  z[3 * H + k] = dh * tc * og * (1.f - og);
+  dcp_out[idx] = dc * fg;
+}
+
+__global__ void lstm_dcarry_kernel(const float* __restrict__ dhp_gemm, const float* __restrict__ dcp, const uint8_t* __restrict__ reset0, int64_t E, int H,
+                                   float* __restrict__ d_carry0) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= E * H) return;
+  const int64_t e = i / H;
+  const int k = (int)(i % H);
+  const bool cut = reset0[e] != 0;
+  d_carry0[e * 2 * H + k] = cut ? 0.f : dcp[i];
+  d_carry0[e * 2 * H + H + k] = cut ? 0.f : dhp_gemm[i];
+}
+
 constexpr size_t kGruSmemLimit = 227 * 1024;
 // launch shape: R = 8 rows per CTA from 1024 sequences up (the rollout step), else 4 with the reduction split over two thread groups
 inline int gru_threads(int H, int ks) { return ((ks * 3 * H + 31) / 32) * 32; }
@@ -494,6 +593,81 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
     simt::reduce_partials_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ws.partials, ws.splits, np, nw, grad_weight, d_w_h, overwrite);
     STX_LAUNCH_OK();
     simt::reduce_partials_kernel<<<(unsigned)((H + 255) / 256), 256, 0, st>>>(ws.partials + nw + 2 * H, ws.splits, np, H, grad_weight, d_b_hn, overwrite);
+    STX_LAUNCH_OK();
+  }
+  return STX_OK;
+}
+
+extern "C" size_t stx_lstm_workspace_bytes(int T, int64_t E, int H) {
+  if (T <= 0 || E <= 0 || H <= 0) return 0;
+  return carve_lstm(T, E, H, nullptr).bytes;
+}
+
+extern "C" int stx_lstm_sequence_forward(const float* gi, const uint8_t* reset, const float* carry0, const float* w_h, int T, int64_t E, int H,
+                                         float* h_seq, float* carry_last, void* workspace, size_t workspace_bytes, void* stream) {
+  STX_REQUIRE(gi && reset && carry0 && w_h && h_seq && workspace, STX_E_ARG, "stx_lstm_sequence_forward: null pointer");
+  STX_REQUIRE(T > 0 && E > 0 && H > 0, STX_E_SHAPE, "stx_lstm_sequence_forward: T=%d E=%lld H=%d", T, (long long)E, H);
+  STX_REQUIRE(workspace_bytes >= stx_lstm_workspace_bytes(T, E, H), STX_E_WORKSPACE, "stx_lstm_sequence_forward: workspace %zu < %zu", workspace_bytes,
+              stx_lstm_workspace_bytes(T, E, H));
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
+  const size_t eh = (size_t)E * H;
+  const unsigned blocks = (unsigned)((eh + 255) / 256);
+  lstm_init_kernel<<<blocks, 256, 0, st>>>(carry0, reset, E, H, ws.cp_seq, ws.hp_seq);
+  STX_LAUNCH_OK();
+  for (int t = 0; t < T; ++t) {
+    simt::GemmArgs g{};
+    g.A = ws.hp_seq + (size_t)t * eh, g.lda = H, g.B = w_h, g.C = ws.gh, g.mask_act = -1;
+    g.M = E, g.N = 4 * H, g.K = H;
+    STX_CUDA_OK(simt::launch_gemm<simt::FWD>(g, 1, st));
+    lstm_gate_fwd_kernel<<<blocks, 256, 0, st>>>(gi + (size_t)t * 4 * eh, ws.gh, ws.cp_seq + (size_t)t * eh, t + 1 < T ? reset + (size_t)(t + 1) * E : nullptr, E, H,
+                                                  h_seq + (size_t)t * eh, ws.cp_seq + (size_t)(t + 1) * eh, ws.hp_seq + (size_t)(t + 1) * eh,
+                                                  ws.gi_ + (size_t)t * eh, ws.gf_ + (size_t)t * eh, ws.gg_ + (size_t)t * eh, ws.go_ + (size_t)t * eh,
+                                                  ws.tc_ + (size_t)t * eh, (t == T - 1) ? carry_last : nullptr);
+    STX_LAUNCH_OK();
+  }
+  return STX_OK;
+}
+
+extern "C" int stx_lstm_sequence_backward(const float* d_h_seq, const uint8_t* reset, const float* w_h, int T, int64_t E, int H, void* workspace,
+                                          size_t workspace_bytes, float* d_gi, float* d_w_h, float grad_weight, int overwrite, float* d_carry0,
+                                          void* stream) {
+  STX_REQUIRE(d_h_seq && reset && w_h && workspace && d_gi, STX_E_ARG, "stx_lstm_sequence_backward: null pointer");
+  STX_REQUIRE(T > 0 && E > 0 && H > 0, STX_E_SHAPE, "stx_lstm_sequence_backward: T=%d E=%lld H=%d", T, (long long)E, H);
+  STX_REQUIRE(workspace_bytes >= stx_lstm_workspace_bytes(T, E, H), STX_E_WORKSPACE, "stx_lstm_sequence_backward: workspace %zu < %zu", workspace_bytes,
+              stx_lstm_workspace_bytes(T, E, H));
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
+  const size_t eh = (size_t)E * H;
+  const unsigned blocks = (unsigned)((eh + 255) / 256);
+  for (int t = T - 1; t >= 0; --t) {
+    const bool last = (t == T - 1);
+    lstm_gate_bwd_kernel<<<blocks, 256, 0, st>>>(d_h_seq + (size_t)t * eh, last ? nullptr : ws.dhp_gemm, last ? nullptr : ws.dcp[(t + 1) & 1],
+                                                  last ? nullptr : reset + (size_t)(t + 1) * E, ws.gi_ + (size_t)t * eh, ws.gf_ + (size_t)t * eh,
+                                                  ws.gg_ + (size_t)t * eh, ws.go_ + (size_t)t * eh, ws.tc_ + (size_t)t * eh, ws.cp_seq + (size_t)t * eh, E, H,
+                                                  d_gi + (size_t)t * 4 * eh, ws.dcp[t & 1]);
+    STX_LAUNCH_OK();
+    if (t > 0 || d_carry0) {
+      simt::GemmArgs d{};
+      d.A = d_gi + (size_t)t * 4 * eh, d.lda = 4 * H, d.B = w_h, d.C = ws.dhp_gemm, d.mask_act = -1;
+      d.M = E, d.N = H, d.K = 4 * H;
+      STX_CUDA_OK(simt::launch_gemm<simt::DX>(d, 1, st));
+    }
+  }
+  if (d_carry0) {
+    lstm_dcarry_kernel<<<blocks, 256, 0, st>>>(ws.dhp_gemm, ws.dcp[0], reset, E, H, d_carry0);
+    STX_LAUNCH_OK();
+  }
+  if (d_w_h) {   // d(W_h) = hp_seq^T d(z)_seq over all (t, e) rows
+    const int64_t rows = (int64_t)T * E;
+    const int64_t np = (int64_t)H * 4 * H;
+    simt::GemmArgs g{};
+    g.A = ws.hp_seq, g.lda = H, g.B = d_gi, g.C = ws.partials, g.dbias = nullptr, g.mask_act = -1;
+    g.M = rows, g.N = 4 * H, g.K = H;
+    g.rows_per_split = (rows + ws.splits - 1) / ws.splits;
+    g.part_stride = np, g.dbias_stride = np;
+    STX_CUDA_OK(simt::launch_gemm<simt::DW>(g, ws.splits, st));
+    simt::reduce_partials_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ws.partials, ws.splits, np, np, grad_weight, d_w_h, overwrite);
     STX_LAUNCH_OK();
   }
   return STX_OK;

@@ -835,3 +835,38 @@ def ppo_head_grads(logits: Optional[torch.Tensor], value: Optional[torch.Tensor]
     _lib.check(lib.stx_ppo_head_grads(_p(logits), _p(value), _p(idx), int(row0), _p(action), _p(logp_old), _p(v_old), _p(adv), _p(targets), _p(adv_stats),
                                       mb, A, float(clip_eps), float(ent_coef), float(vf_coef), _p(d_logits), _p(d_value), _p(metrics), float(weight),
                                       _p(scratch), _stream()), "stx_ppo_head_grads")
+
+
+def lstm_workspace(T: int, E: int, H: int, device) -> torch.Tensor:
+    return torch.zeros(int(_lib.load().stx_lstm_workspace_bytes(int(T), int(E), int(H))), dtype=torch.uint8, device=device)
+
+
+def lstm_sequence_forward(gi: torch.Tensor, reset: torch.Tensor, carry0: torch.Tensor, w_h: torch.Tensor, ws: torch.Tensor,
+                          out: Optional[torch.Tensor] = None, carry_last: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ScannedRNN(lstm) over (T, E): gi (T, E, 4H), carry0 (E, 2H) = (c | h), w_h (H, 4H) -> h_seq (T, E, H); carry_last (E, 2H) optional."""
+    dev = _need_cuda(gi, reset, carry0, w_h, ws, out, carry_last)
+    T, E, H4 = gi.shape
+    H = H4 // 4
+    r8 = reset.view(torch.uint8) if reset.dtype == torch.bool else reset
+    for t_, shape, name in ((gi, (T, E, 4 * H), "gi"), (carry0, (E, 2 * H), "carry0"), (w_h, (H, 4 * H), "w_h")):
+        if t_.dtype != torch.float32 or tuple(t_.shape) != shape or not t_.is_contiguous():
+            raise StxError(f"lstm_sequence_forward: {name} must be contiguous float32 {shape}")
+    if r8.dtype != torch.uint8 or tuple(r8.shape) != (T, E) or not r8.is_contiguous():
+        raise StxError("lstm_sequence_forward: reset must be contiguous uint8 / bool (T, E)")
+    if out is None:
+        out = torch.empty(T, E, H, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().stx_lstm_sequence_forward(_p(gi), _p(r8), _p(carry0), _p(w_h), T, E, H, _p(out), _p(carry_last), _p(ws), ws.numel(), _stream()),
+               "stx_lstm_sequence_forward")
+    return out
+
+
+def lstm_sequence_backward(d_h_seq: torch.Tensor, reset: torch.Tensor, w_h: torch.Tensor, ws: torch.Tensor, d_gi: torch.Tensor,
+                           d_w_h: Optional[torch.Tensor] = None, grad_weight: float = 1.0, overwrite: bool = True,
+                           d_carry0: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(d_h_seq, reset, w_h, ws, d_gi, d_w_h, d_carry0)
+    T, E, H = d_h_seq.shape
+    r8 = reset.view(torch.uint8) if reset.dtype == torch.bool else reset
+    if d_h_seq.dtype != torch.float32 or not d_h_seq.is_contiguous() or d_gi.dtype != torch.float32 or d_gi.numel() != T * E * 4 * H:
+        raise StxError("lstm_sequence_backward: d_h_seq (T, E, H) / d_gi (T, E, 4H) must be contiguous float32")
+    _lib.check(_lib.load().stx_lstm_sequence_backward(_p(d_h_seq), _p(r8), _p(w_h), T, E, H, _p(ws), ws.numel(), _p(d_gi), _p(d_w_h), float(grad_weight),
+                                                      int(bool(overwrite)), _p(d_carry0), _stream()), "stx_lstm_sequence_backward")

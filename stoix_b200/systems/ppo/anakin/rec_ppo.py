@@ -54,7 +54,7 @@ def _world() -> Tuple[int, int]:
 class _Shard:
     """Trajectory of one (device, update-batch) shard, time-major (RNNPPOTransition fields + the carried row T)."""
 
-    def __init__(self, T: int, E: int, D: int, H: int, device):
+    def __init__(self, T: int, E: int, D: int, H: int, device):   # H = carry width (2 x hidden for lstm)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
         self.obs = z(T + 1, E, D)                       # row t = last_timestep.observation of step t, row T = the carry
         self.done, self.trunc = z(T + 1, E, dt=torch.uint8), z(T + 1, E, dt=torch.uint8)   # flags BEFORE step t
@@ -82,10 +82,10 @@ class _NetWs:
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         M, H = chunk * C, lay.H
         self.ws_pre, self.ws_post = ops.mlp_train_workspace(lay.spec_pre, M, device), ops.mlp_train_workspace(lay.spec_post, M, device)
-        self.ws_gru = ops.gru_workspace(chunk, C, H, device)
-        self.gi, self.d_gi = z(chunk, C, 3 * H), z(chunk, C, 3 * H)
+        self.ws_gru = (ops.lstm_workspace if lay.cell_type == "lstm" else ops.gru_workspace)(chunk, C, H, device)
+        self.gi, self.d_gi = z(chunk, C, lay.G * H), z(chunk, C, lay.G * H)
         self.h_seq, self.d_h = z(chunk, C, H), z(chunk, C, H)
-        self.h0 = z(C, H)
+        self.h0 = z(C, lay.S)
         self.out, self.d_out = z(M, out_dim), z(M, out_dim)
 
 
@@ -121,7 +121,7 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
         a_tree, c_tree = state.params.actor_params, state.params.critic_params
         la, lc = a_tree.layout, c_tree.layout
         dev = a_tree.flat.device
-        D, A, H = la.spec_pre.sizes[0], la.spec_post.sizes[-1], la.H
+        D, A, H = la.spec_pre.sizes[0], la.spec_post.sizes[-1], la.S   # H: carry width
         coff = _pad8(la.param_count)
         total = coff + _pad8(lc.param_count)
         plan = ops.AdamPlan([(0, la.param_count, actor_opt.init_lr, actor_opt.max_grad_norm), (coff, lc.param_count, critic_opt.init_lr, critic_opt.max_grad_norm)],
@@ -202,9 +202,13 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
         pre, w_h, b_hn, post = lay.blocks(p_flat)
         g_pre, g_wh, g_bhn, g_post = lay.blocks(g_flat)
         obs_flat = sh.obs[:T].reshape(T * E, D)
-        ops.mlp_forward_train(lay.spec_pre, pre, obs_flat, w.ws_pre, out=w.gi.view(chunk * C, 3 * H), row_idx=idx)
-        ops.gather_rows(h_store.reshape(T * E, H), idx[:C], w.h0)                        # hstates[0] of the chunk (:216-218)
-        ops.gru_sequence_forward(w.gi, b["reset_mb"], w.h0, w_h, b_hn, w.ws_gru, out=w.h_seq)
+        lstm = lay.cell_type == "lstm"
+        ops.mlp_forward_train(lay.spec_pre, pre, obs_flat, w.ws_pre, out=w.gi.view(chunk * C, lay.G * H), row_idx=idx)
+        ops.gather_rows(h_store.reshape(T * E, lay.S), idx[:C], w.h0)                    # hstates[0] of the chunk (:216-218)
+        if lstm:
+            ops.lstm_sequence_forward(w.gi, b["reset_mb"], w.h0, w_h, w.ws_gru, out=w.h_seq)
+        else:
+            ops.gru_sequence_forward(w.gi, b["reset_mb"], w.h0, w_h, b_hn, w.ws_gru, out=w.h_seq)
         ops.mlp_forward_train(lay.spec_post, post, w.h_seq.view(chunk * C, H), w.ws_post, out=w.out)
         stats = sh.adv_stats if sysc.standardize_advantages else None
         ops.ppo_head_grads(w.out if is_actor else None, None if is_actor else w.out, idx, sh.action.reshape(-1), sh.log_prob.reshape(-1),
@@ -213,8 +217,11 @@ def get_learner_fn(env: Environment, apply_fns: Tuple[Callable, Callable], updat
                            scratch_key="ppo_head_actor" if is_actor else "ppo_head_critic")
         ops.mlp_backward(lay.spec_post, post, w.h_seq.view(chunk * C, H), w.d_out, w.ws_post, net_grad=g_post, grad_weight=weight, overwrite=overwrite,
                          d_input=w.d_h.view(chunk * C, H))
-        ops.gru_sequence_backward(w.d_h, b["reset_mb"], w_h, w.ws_gru, w.d_gi, d_w_h=g_wh, d_b_hn=g_bhn, grad_weight=weight, overwrite=overwrite)
-        ops.mlp_backward(lay.spec_pre, pre, obs_flat, w.d_gi.view(chunk * C, 3 * H), w.ws_pre, net_grad=g_pre, grad_weight=weight, overwrite=overwrite,
+        if lstm:
+            ops.lstm_sequence_backward(w.d_h, b["reset_mb"], w_h, w.ws_gru, w.d_gi, d_w_h=g_wh, grad_weight=weight, overwrite=overwrite)
+        else:
+            ops.gru_sequence_backward(w.d_h, b["reset_mb"], w_h, w.ws_gru, w.d_gi, d_w_h=g_wh, d_b_hn=g_bhn, grad_weight=weight, overwrite=overwrite)
+        ops.mlp_backward(lay.spec_pre, pre, obs_flat, w.d_gi.view(chunk * C, lay.G * H), w.ws_pre, net_grad=g_pre, grad_weight=weight, overwrite=overwrite,
                          row_idx=idx)
 
     def _minibatch_grads(state: RNNLearnerState, u: int, cols: torch.Tensor, metrics: torch.Tensor, overwrite: bool) -> None:
@@ -395,7 +402,7 @@ def get_rnn_evaluator_fn(env: Environment, actor_network: RecurrentActor, config
         keys = srandom.split(key, n_episodes + 1)
         state, ts = env.reset(keys[:n_episodes])
         dev = ts.observation.device
-        h = torch.zeros(n_episodes, actor_network.hidden_state_dim, device=dev)
+        h = actor_network.rnn.initialize_carry(n_episodes, dev)
         reset = torch.zeros(n_episodes, dtype=torch.bool, device=dev)
         alive = torch.ones(n_episodes, dtype=torch.bool, device=dev)
         ret, length = torch.zeros(n_episodes, device=dev), torch.zeros(n_episodes, dtype=torch.int32, device=dev)

@@ -139,3 +139,42 @@ def test_minibatch_gradients_match_autograd_with_reference_quirks():
         for name, got in (("W0", g.pre.W[0]), ("bi", g.pre.b[1]), ("Wh", g.Wh), ("bhn", g.bhn), ("W1", g.post.W[0]), ("b2", g.post.b[1])):
             np.testing.assert_allclose(got, tn[name].grad.numpy(), rtol=1e-8, atol=1e-11, err_msg=name)
     np.testing.assert_allclose(info["value_loss"], float(loss_c) / 0.5, rtol=1e-10)
+
+
+def test_lstm_recurrence_matches_autograd():
+    """flax LSTMCell formula in torch ops, carry = (c | h) zeroed at resets, vs oracle lstm_forward / lstm_backward and the whole net."""
+    rng = np.random.default_rng(4)
+    T, E, D, P, H, Q, A = 7, 5, 4, 6, 3, 5, 2
+    pre = O.MLPParams([rng.standard_normal((D, P)) * 0.3, rng.standard_normal((P, 4 * H)) * 0.3], [rng.standard_normal(P) * 0.1, rng.standard_normal(4 * H) * 0.1], "silu")
+    post = O.MLPParams([rng.standard_normal((H, Q)) * 0.3, rng.standard_normal((Q, A)) * 0.3], [rng.standard_normal(Q) * 0.1, rng.standard_normal(A) * 0.1], "silu")
+    net = R.RecNet(pre, rng.standard_normal((H, 4 * H)) * 0.3, np.zeros(0), post)
+    assert net.is_lstm
+    obs, carry0 = rng.standard_normal((T, E, D)), rng.standard_normal((E, 2 * H))
+    reset = rng.random((T, E)) < 0.25
+    d_out = rng.standard_normal((T, E, A))
+    out, last, cache = R.rec_forward(net, carry0, obs, reset)
+    g = R.rec_backward(net, cache, d_out)
+    t = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    tn = {"W0": t(pre.W[0]), "b0": t(pre.b[0]), "Wi": t(pre.W[1]), "bi": t(pre.b[1]), "Wh": t(net.Wh), "W1": t(post.W[0]), "b1": t(post.b[0]),
+          "W2": t(post.W[1]), "b2": t(post.b[1])}
+    silu = torch.nn.functional.silu
+    gi = silu(torch.tensor(obs) @ tn["W0"] + tn["b0"]) @ tn["Wi"] + tn["bi"]
+    c, h = torch.tensor(carry0[:, :H]), torch.tensor(carry0[:, H:])
+    hs = []
+    for k in range(T):
+        m = torch.tensor(reset[k])[:, None]
+        c, h = torch.where(m, torch.zeros_like(c), c), torch.where(m, torch.zeros_like(h), h)
+        z = gi[k] + h @ tn["Wh"]
+        i_, f_, g_, o_ = torch.sigmoid(z[:, :H]), torch.sigmoid(z[:, H:2 * H]), torch.tanh(z[:, 2 * H:3 * H]), torch.sigmoid(z[:, 3 * H:])
+        c = f_ * c + i_ * g_
+        h = o_ * torch.tanh(c)
+        hs.append(h)
+    to = silu(torch.stack(hs) @ tn["W1"] + tn["b1"]) @ tn["W2"] + tn["b2"]
+    np.testing.assert_allclose(out, to.detach().numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(last, torch.cat([c, h], 1).detach().numpy(), rtol=1e-10, atol=1e-12)
+    (to * torch.tensor(d_out)).sum().backward()
+    for name, got in (("W0", g.pre.W[0]), ("Wi", g.pre.W[1]), ("bi", g.pre.b[1]), ("Wh", g.Wh), ("W1", g.post.W[0]), ("b2", g.post.b[1])):
+        np.testing.assert_allclose(got, tn[name].grad.numpy(), rtol=1e-9, atol=1e-11, err_msg=name)
+    net2 = R.RecNet.from_flat(net.flat(), (D, P, 4 * H), H, (H, Q, A))
+    np.testing.assert_array_equal(net2.flat(), net.flat())
+    assert net2.is_lstm

@@ -140,11 +140,13 @@ def test_recurrent_faces_and_parameter_tree():
     np.testing.assert_allclose(f64(pi.log_prob(a)), O.categorical_log_prob(out_o, a.cpu().numpy()), rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("chunk", [None, 8])
-def test_update_steps_match_oracle(chunk):
+@pytest.mark.parametrize("chunk,cell", [(None, "gru"), (8, "gru"), (8, "lstm")])
+def test_update_steps_match_oracle(chunk, cell):
     from stoix_b200 import ops
 
-    cfg = _cfg([] if chunk is None else [f"system.recurrent_chunk_size={chunk}"])
+    cfg = _cfg(([] if chunk is None else [f"system.recurrent_chunk_size={chunk}"])
+               + [f"network.actor_network.rnn_layer.cell_type={cell}", f"network.critic_network.rnn_layer.cell_type={cell}"])
+    S = 16 if cell == "gru" else 32     # carry width: lstm carries (c | h)
     rec_ppo, learn, actor_network, state = _setup(cfg)
     cfg.arch.num_updates_per_eval = 1     # one update per learn() call; arch.num_updates (3) still drives the LR schedule
     T, E, nmb, epochs = 16, 32, 4, 2
@@ -155,7 +157,7 @@ def test_update_steps_match_oracle(chunk):
     a_st, c_st = O.AdamState(np.zeros(n_a), np.zeros(n_a)), O.AdamState(np.zeros(n_c), np.zeros(n_c))
     hyp = O.PPOHyper(ent_coef=float(cfg.system.ent_coef), actor_lr=float(cfg.system.actor_lr), critic_lr=float(cfg.system.critic_lr), epochs=epochs,
                      num_minibatches=nmb, num_updates=int(cfg.arch.num_updates))
-    h_a, h_c = np.zeros((E, 16)), np.zeros((E, 16))
+    h_a, h_c = np.zeros((E, S)), np.zeros((E, S))
     for upd in range(2):
         out = learn(state)
         state = out.learner_state
@@ -169,7 +171,7 @@ def test_update_steps_match_oracle(chunk):
         else:   # row 0 of this rollout = row T of the previous one (observation and flags carried over)
             np.testing.assert_array_equal(obs[0], carry[0]), np.testing.assert_array_equal(done[0], carry[1]), np.testing.assert_array_equal(trunc[0], carry[2])
         action, reward = sh.action.cpu().numpy(), f64(sh.reward)
-        val, lp, hs_a, hs_c = np.zeros((T, E)), np.zeros((T, E)), np.zeros((T, E, 16)), np.zeros((T, E, 16))
+        val, lp, hs_a, hs_c = np.zeros((T, E)), np.zeros((T, E)), np.zeros((T, E, S)), np.zeros((T, E, S))
         for t in range(T):
             reset = (done[t] | trunc[t])[None]
             lg, h_a, _ = R.rec_forward(actor, h_a, obs[t][None], reset)
@@ -224,3 +226,26 @@ def test_experiment_runs_on_cartpole():
                                       "arch.total_timesteps=8192", "arch.num_evaluation=2", "arch.num_eval_episodes=16", "arch.max_eval_steps=100",
                                       "logger.use_console=False"], config_dir="default/anakin")
     assert np.isfinite(rec_ppo.run_experiment(cfg))
+
+
+@pytest.mark.parametrize("T,E,H", [(6, 40, 12), (1, 64, 128), (9, 130, 32)])
+def test_lstm_sequence_matches_oracle(T, E, H):
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(T * 10 + H)
+    gi, c0 = rng.standard_normal((T, E, 4 * H)).astype(np.float32), rng.standard_normal((E, 2 * H)).astype(np.float32)
+    Wh = (rng.standard_normal((H, 4 * H)) * 0.2).astype(np.float32)
+    reset = rng.random((T, E)) < 0.2
+    d_h = rng.standard_normal((T, E, H)).astype(np.float32)
+    ws = ops.lstm_workspace(T, E, H, "cuda")
+    last = torch.zeros(E, 2 * H, device="cuda")
+    h_seq = ops.lstm_sequence_forward(dev(gi), dev(reset, torch.uint8), dev(c0), dev(Wh), ws, carry_last=last)
+    hs_o, last_o, cache = R.lstm_forward(gi.astype(np.float64), reset, c0.astype(np.float64), Wh.astype(np.float64))
+    np.testing.assert_allclose(f64(h_seq), hs_o, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(f64(last), last_o, rtol=2e-5, atol=2e-6)
+    d_gi, d_wh, d_c0 = torch.zeros(T, E, 4 * H, device="cuda"), torch.full((H, 4 * H), 3.0, device="cuda"), torch.zeros(E, 2 * H, device="cuda")
+    ops.lstm_sequence_backward(dev(d_h), dev(reset, torch.uint8), dev(Wh), ws, d_gi, d_w_h=d_wh, grad_weight=0.25, overwrite=False, d_carry0=d_c0)
+    dgi_o, dWh_o, dc0_o = R.lstm_backward(cache, reset, d_h.astype(np.float64), Wh.astype(np.float64))
+    np.testing.assert_allclose(f64(d_gi), dgi_o, rtol=1e-4, atol=1e-5)
+    assert rel(f64(d_wh), 3.0 + 0.25 * dWh_o) < 1e-5
+    np.testing.assert_allclose(f64(d_c0), dc0_o, rtol=1e-4, atol=1e-5)
