@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--minibatches", type=int, default=16)
     ap.add_argument("--updates", type=int, default=2)
+    ap.add_argument("--cell", default="gru")
     a = ap.parse_args()
     from stoix_b200 import _lib, random as srandom
     from stoix_b200.config import compose
@@ -28,7 +29,8 @@ def main():
     torch.cuda.set_device(0)
     cfg = compose("default_rec_ppo", ["env=synthetic/box", "env.kwargs.obs_dim=32", "env.kwargs.num_actions=8", f"arch.total_num_envs={a.envs}",
                                       f"system.rollout_length={a.rollout}", f"system.epochs={a.epochs}", f"system.num_minibatches={a.minibatches}",
-                                      f"arch.total_timesteps={a.envs * a.rollout * (a.updates + 2)}", "arch.num_evaluation=1", "logger.use_console=False"],
+                                      f"arch.total_timesteps={a.envs * a.rollout * (a.updates + 2)}", "arch.num_evaluation=1", "logger.use_console=False",
+                                      f"network.actor_network.rnn_layer.cell_type={a.cell}", f"network.critic_network.rnn_layer.cell_type={a.cell}"],
                   config_dir="default/anakin")
     cfg.num_devices, cfg.rank = 1, 0
     cfg = check_total_timesteps(cfg, quiet=True)
@@ -61,7 +63,7 @@ def main():
     print(json.dumps({"metric": "env steps/sec rec_ppo Anakin (synthetic Box, GRU actor-critic)", "value": steps / ms * 1e3, "unit": "env_steps/s",
                       "ms_per_update": ms, "n_gpus": 1, "phase_ms": phase, "stx_launches_per_update": launches,
                       "config": {"workload": f"rec_ppo, obs_dim=32, envs={a.envs}, rollout={a.rollout}, epochs={a.epochs}, minibatches={a.minibatches}, "
-                                             "pre MLP[128] silu -> GRU(128) -> post MLP[128] silu, fp32", "dtype": "f32", "cuda_graph": bool(cfg.arch.get("cuda_graph", True)), "phase_ms_note": "phases timed eagerly, ms_per_update from graph replays"}}))
+                                             f"pre MLP[128] silu -> {a.cell.upper()}(128) -> post MLP[128] silu, fp32", "dtype": "f32", "cuda_graph": bool(cfg.arch.get("cuda_graph", True)), "phase_ms_note": "phases timed eagerly, ms_per_update from graph replays"}}))
 
 
 if __name__ == "__main__":

@@ -14,6 +14,8 @@
 // sequence kernel (W_h resident in shared memory, h in registers) would have.  Backward: the gate kernel of step t turns
 // d(h_t) into d(gi_t), d(gh_t); d(h_{t-1}) = d(gh_t) W_h^T + d(h_t) z_t (masked by reset_t); d(W_h) = sum_t hp_t^T d(gh_t) is ONE
 // GEMM over the stored sequences after the loop (fixed summation order: deterministic).
+#include <cooperative_groups.h>
+
 #include "stx_common.cuh"
 #include "stx_simt_gemm.cuh"
 
@@ -468,6 +470,274 @@ __global__ void lstm_dcarry_kernel(const float* __restrict__ dhp_gemm, const flo
   d_carry0[e * 2 * H + H + k] = cut ? 0.f : dhp_gemm[i];
 }
 
+// ---- LSTM, persistent form on a 2-CTA thread-block cluster ---------------------------------------------------------------
+// W_h (H x 4H fp32 = 262 KB at H = 128) does not fit one SM, so a CLUSTER of two CTAs shares each tile of R sequences: CTA q owns
+// the hidden units [q H/2, (q+1) H/2) -- all four gate columns of those units, 131 KB of W_h -- computes their gates and cell
+// update, and after every step pushes its half of the new h into the PEER's shared memory (distributed shared memory) next to its
+// own, into the buffer the next step reads (two h buffers alternate, so a fast CTA never overwrites what its peer still reads);
+// one cluster barrier per step replaces the block barrier.  Backward: each CTA forms d(z) of its units, multiplies with its
+// 2H columns of W_h^T for ALL H outputs and sends the half that belongs to the peer's units across; the two partial sums are
+// added in rank order (deterministic).  No per-step launch, no global synchronisation.
+namespace cg = cooperative_groups;
+constexpr int kLstmR = 4, kLstmKS = 2;
+struct LstmSmem {
+  __host__ __device__ static size_t w_floats(int H) { return ((size_t)H * (2 * H + 1) + 3) / 4 * 4; }
+  static size_t fwd_bytes(int H) { return (w_floats(H) + 2 * (size_t)H * kLstmR + (size_t)(H / 2) * kLstmR + (size_t)kLstmKS * kLstmR * 2 * H) * 4; }
+  static size_t bwd_bytes(int H) {
+    return (w_floats(H) + (size_t)2 * H * kLstmR + 2 * (size_t)kLstmKS * kLstmR * H + 2 * (size_t)kLstmR * (H / 2) + 2 * (size_t)kLstmR * (H / 2)) * 4;
+  }
+};
+
+// this CTA's 2H columns of W_h: local column g * Hq + jl  <->  global column g * H + q * Hq + jl
+__device__ __forceinline__ void lstm_load_w(float* __restrict__ Ws, const float* __restrict__ w_h, int H, int q) {
+  const int Hq = H / 2, nl = 2 * H, total = H * nl;
+  constexpr int U = 8;
+  for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < total) {
+        const int k = i / nl, c = i % nl;
+        v[u] = __ldg(w_h + (size_t)k * 4 * H + (c / Hq) * H + q * Hq + c % Hq);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < total) Ws[(i / nl) * (nl + 1) + i % nl] = v[u];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    lstm_seq_fwd_kernel(const float* __restrict__ gi, const uint8_t* __restrict__ reset, const float* __restrict__ carry0, const float* __restrict__ w_h,
+                        int T, int64_t E, int H, float* __restrict__ h_seq, float* __restrict__ carry_last, float* __restrict__ hp_seq,
+                        float* __restrict__ cp_seq, float* __restrict__ si, float* __restrict__ sf, float* __restrict__ sg, float* __restrict__ so,
+                        float* __restrict__ stc) {
+  constexpr int R = kLstmR, KS = kLstmKS;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  extern __shared__ __align__(16) float gsm[];
+  const int Hq = H / 2, nl = 2 * H;
+  float* Ws = gsm;                                  // [H][2H + 1]
+  float* hs = Ws + LstmSmem::w_floats(H);           // [2][H][R]  full h entering the step (k-major), two alternating buffers
+  float* cs = hs + 2 * (size_t)H * R;               // [Hq][R]    c of this CTA's units
+  float* ghp = cs + (size_t)Hq * R;                 // [KS][R][2H] partial products
+  float* hs_peer = cluster.map_shared_rank(hs, q ^ 1);
+  const int kh = threadIdx.x / nl, n = threadIdx.x % nl;
+  const int kper = (H + KS - 1) / KS;
+  const int k_begin = kh * kper, k_end = (k_begin + kper < H) ? k_begin + kper : H;
+  const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
+  const int items = Hq * R;
+  const int64_t eh = E * (int64_t)H;
+  lstm_load_w(Ws, w_h, H, q);
+  for (int i = threadIdx.x; i < H * R; i += blockDim.x) {     // every CTA initialises the FULL h of buffer 0 itself
+    const int r = i / H, j = i % H;
+    const int64_t row = row0 + r;
+    float hv = 0.f;
+    if (row < E && !reset[row]) hv = carry0[row * 2 * H + H + j];
+    hs[j * R + r] = hv;
+    if (row < E && j / Hq == q) {
+      const float cv = reset[row] ? 0.f : carry0[row * 2 * H + j];
+      cs[(j - q * Hq) * R + r] = cv;
+      hp_seq[row * H + j] = hv, cp_seq[row * H + j] = cv;
+    } else if (row >= E && j / Hq == q) {
+      cs[(j - q * Hq) * R + r] = 0.f;
+    }
+  }
+  cluster.sync();
+  for (int t = 0; t < T; ++t) {
+    const float* hcur = hs + (size_t)(t & 1) * H * R;
+    const size_t nxt = (size_t)((t + 1) & 1) * H * R;
+    // requests for the gate phase (one item per thread: Hq * R <= blockDim)
+    float gz[4] = {0.f, 0.f, 0.f, 0.f};
+    bool cut = false;
+    const int i0 = threadIdx.x;
+    const int r0 = i0 / Hq, jl0 = i0 % Hq;
+    const int64_t rowg = row0 + r0;
+    if (i0 < items && rowg < E) {
+      const float* a = gi + ((int64_t)t * E + rowg) * 4 * H + q * Hq + jl0;
+      gz[0] = __ldg(a), gz[1] = __ldg(a + H), gz[2] = __ldg(a + 2 * H), gz[3] = __ldg(a + 3 * H);
+      cut = (t + 1 < T) && reset[(int64_t)(t + 1) * E + rowg] != 0;
+    }
+    if (kh < KS) {
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      const float* wcol = Ws + n;
+#pragma unroll 4
+      for (int k = k_begin; k < k_end; ++k) {
+        const float w = wcol[(size_t)k * (nl + 1)];
+        const float4 hv = *reinterpret_cast<const float4*>(hcur + k * R);
+        acc[0] = fmaf(w, hv.x, acc[0]), acc[1] = fmaf(w, hv.y, acc[1]), acc[2] = fmaf(w, hv.z, acc[2]), acc[3] = fmaf(w, hv.w, acc[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) ghp[((size_t)kh * R + r) * nl + n] = acc[r];
+    }
+    __syncthreads();
+    if (i0 < items) {
+      const int j = q * Hq + jl0;
+      float h = 0.f, hn = 0.f;
+      if (rowg < E) {
+        float z[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float b = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) b += ghp[((size_t)kk * R + r0) * nl + g * Hq + jl0];   // fixed order
+          z[g] = gz[g] + b;
+        }
+        const float ig = sigm(z[0]), fg = sigm(z[1]), gg = tanhf(z[2]), og = sigm(z[3]);
+        const float c = fg * cs[jl0 * R + r0] + ig * gg;
+        const float tc = tanhf(c);
+        h = og * tc;
+        const int64_t o = (int64_t)t * eh + rowg * H + j;
+        h_seq[o] = h, si[o] = ig, sf[o] = fg, sg[o] = gg, so[o] = og, stc[o] = tc;
+        hn = cut ? 0.f : h;
+        const float cn = cut ? 0.f : c;
+        hp_seq[o + eh] = hn, cp_seq[o + eh] = cn;
+        cs[jl0 * R + r0] = cn;
+        if (t == T - 1 && carry_last) carry_last[rowg * 2 * H + j] = c, carry_last[rowg * 2 * H + H + j] = h;
+      }
+      hs[nxt + (size_t)j * R + r0] = hn;         // my half of the next step's h: here ...
+      hs_peer[nxt + (size_t)j * R + r0] = hn;    // ... and in the peer's shared memory
+    }
+    cluster.sync();   // both halves of h_{t+1} are in place in both CTAs; also this block's barrier
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    lstm_seq_bwd_kernel(const float* __restrict__ d_h_seq, const uint8_t* __restrict__ reset, const float* __restrict__ w_h, int T, int64_t E, int H,
+                        const float* __restrict__ cp_seq, const float* __restrict__ si, const float* __restrict__ sf, const float* __restrict__ sg,
+                        const float* __restrict__ so, const float* __restrict__ stc, float* __restrict__ d_gi, float* __restrict__ d_carry0) {
+  constexpr int R = kLstmR, KS = kLstmKS;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  extern __shared__ __align__(16) float gsm[];
+  const int Hq = H / 2, nl = 2 * H;
+  float* Ws = gsm;                                  // [H][2H + 1]  (this CTA's columns)
+  float* dzT = Ws + LstmSmem::w_floats(H);          // [2H][R]   d(z_t) of this CTA's units, column-major
+  float* part = dzT + (size_t)nl * R;               // [2 KS][R][H]... laid out as [blk][R][H]: partial d(z) W^T over this CTA's column blocks
+  float* inbox = part + 2 * (size_t)KS * R * H;     // [2][R][Hq]  the peer's partial sums for MY units (two alternating buffers)
+  float* dh_rec = inbox + 2 * (size_t)R * Hq;       // [R][Hq]
+  float* dc_rec = dh_rec + (size_t)R * Hq;          // [R][Hq]
+  float* inbox_peer = cluster.map_shared_rank(inbox, q ^ 1);
+  const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
+  const int64_t eh = E * (int64_t)H;
+  const int items = Hq * R;
+  lstm_load_w(Ws, w_h, H, q);
+  for (int i = threadIdx.x; i < items; i += blockDim.x) dh_rec[i] = 0.f, dc_rec[i] = 0.f;
+  const int i0 = threadIdx.x;
+  const int r0 = i0 / Hq, jl0 = i0 % Hq;
+  const int64_t rowg = row0 + r0;
+  const int j0 = q * Hq + jl0;
+  float v_dh = 0.f, v_i = 0.f, v_f = 0.f, v_g = 0.f, v_o = 0.f, v_tc = 0.f, v_cp = 0.f;
+  bool v_cut = false;
+  auto request = [&](int t) {
+    v_dh = v_i = v_f = v_g = v_o = v_tc = v_cp = 0.f, v_cut = false;
+    if (i0 < items && rowg < E && t >= 0) {
+      const int64_t o = (int64_t)t * eh + rowg * H + j0;
+      v_dh = __ldg(d_h_seq + o), v_i = __ldg(si + o), v_f = __ldg(sf + o), v_g = __ldg(sg + o), v_o = __ldg(so + o), v_tc = __ldg(stc + o);
+      v_cp = __ldg(cp_seq + o);
+      v_cut = reset[(int64_t)t * E + rowg] != 0;
+    }
+  };
+  request(T - 1);
+  cluster.sync();
+  const int NB = 2 * KS;                     // column blocks of this CTA's 2H columns
+  const int kcol = (nl + NB - 1) / NB;
+  for (int t = T - 1; t >= 0; --t) {
+    bool cut_t = v_cut;
+    float dcp = 0.f;
+    if (i0 < items) {
+      float dz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (rowg < E) {
+        const float dh = v_dh + dh_rec[r0 * Hq + jl0];
+        const float dc = dc_rec[r0 * Hq + jl0] + dh * v_o * (1.f - v_tc * v_tc);
+        dz[0] = dc * v_g * v_i * (1.f - v_i);
+        dz[1] = dc * v_cp * v_f * (1.f - v_f);
+        dz[2] = dc * v_i * (1.f - v_g * v_g);
+        dz[3] = dh * v_tc * v_o * (1.f - v_o);
+        dcp = dc * v_f;
+        float* a = d_gi + ((int64_t)t * E + rowg) * 4 * H + j0;
+        a[0] = dz[0], a[H] = dz[1], a[2 * H] = dz[2], a[3 * H] = dz[3];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dzT[(size_t)(g * Hq + jl0) * R + r0] = dz[g];
+    }
+    request(t - 1);
+    __syncthreads();
+    if ((int)threadIdx.x < NB * H) {           // partial d(z) W^T over this CTA's columns, for ALL H outputs k
+      const int k = threadIdx.x % H, blk = threadIdx.x / H;
+      const int c0 = blk * kcol, c1 = (c0 + kcol < nl) ? c0 + kcol : nl;
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      const float* wrow = Ws + (size_t)k * (nl + 1);
+#pragma unroll 4
+      for (int nn = c0; nn < c1; ++nn) {
+        const float w = wrow[nn];
+        const float4 dv = *reinterpret_cast<const float4*>(dzT + (size_t)nn * R);
+        acc[0] = fmaf(w, dv.x, acc[0]), acc[1] = fmaf(w, dv.y, acc[1]), acc[2] = fmaf(w, dv.z, acc[2]), acc[3] = fmaf(w, dv.w, acc[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
+    }
+    __syncthreads();
+    // my partial for the PEER's units goes into its inbox; my partial for my own units stays in a register
+    float mine = 0.f;
+    float* box = inbox + (size_t)(t & 1) * R * Hq;
+    if (i0 < items) {
+      float other = 0.f;
+      const int jp = (q ^ 1) * Hq + jl0;
+      for (int blk = 0; blk < NB; ++blk) {       // fixed order
+        mine += part[((size_t)blk * R + r0) * H + j0];
+        other += part[((size_t)blk * R + r0) * H + jp];
+      }
+      inbox_peer[(size_t)(t & 1) * R * Hq + r0 * Hq + jl0] = other;
+    }
+    cluster.sync();
+    if (i0 < items) {
+      const float theirs = box[r0 * Hq + jl0];
+      const float dhp = (q == 0) ? (mine + theirs) : (theirs + mine);   // rank-0 partial first on both CTAs
+      const bool keep = rowg < E && !cut_t;
+      dh_rec[r0 * Hq + jl0] = keep ? dhp : 0.f;
+      dc_rec[r0 * Hq + jl0] = keep ? dcp : 0.f;
+    }
+    __syncthreads();
+  }
+  if (d_carry0 && i0 < items && rowg < E) {
+    d_carry0[rowg * 2 * H + j0] = dc_rec[r0 * Hq + jl0];
+    d_carry0[rowg * 2 * H + H + j0] = dh_rec[r0 * Hq + jl0];
+  }
+  cluster.sync();   // no CTA exits while its peer may still write into its shared memory
+}
+
+inline int lstm_threads(int H) { return ((kLstmKS * 2 * H + 31) / 32) * 32; }
+inline bool lstm_cluster_ok(int H, int64_t E) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("STX_LSTM_CLUSTER");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  (void)E;
+  return enabled && H >= 2 && H % 2 == 0 && lstm_threads(H) <= 1024 && (H / 2) * kLstmR <= lstm_threads(H) && 2 * kLstmKS * H <= lstm_threads(H) &&
+         LstmSmem::fwd_bytes(H) <= 227 * 1024 && LstmSmem::bwd_bytes(H) <= 227 * 1024;
+}
+template <typename... Args>
+inline cudaError_t launch_cluster2(void (*kernel)(Args...), unsigned clusters, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 constexpr size_t kGruSmemLimit = 227 * 1024;
 // launch shape: R = 8 rows per CTA from 1024 sequences up (the rollout step), else 4 with the reduction split over two thread groups
 inline int gru_threads(int H, int ks) { return ((ks * 3 * H + 31) / 32) * 32; }
@@ -613,6 +883,12 @@ extern "C" int stx_lstm_sequence_forward(const float* gi, const uint8_t* reset, 
   LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
+  if (lstm_cluster_ok(H, E)) {
+    STX_CUDA_OK(launch_cluster2(lstm_seq_fwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), lstm_threads(H), LstmSmem::fwd_bytes(H), st, gi, reset, carry0, w_h,
+                                T, E, H, h_seq, carry_last, ws.hp_seq, ws.cp_seq, ws.gi_, ws.gf_, ws.gg_, ws.go_, ws.tc_));
+    STX_LAUNCH_OK();
+    return STX_OK;
+  }
   lstm_init_kernel<<<blocks, 256, 0, st>>>(carry0, reset, E, H, ws.cp_seq, ws.hp_seq);
   STX_LAUNCH_OK();
   for (int t = 0; t < T; ++t) {
@@ -640,7 +916,14 @@ extern "C" int stx_lstm_sequence_backward(const float* d_h_seq, const uint8_t* r
   LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  for (int t = T - 1; t >= 0; --t) {
+  const bool clustered = lstm_cluster_ok(H, E);
+  if (clustered) {
+    STX_CUDA_OK(launch_cluster2(lstm_seq_bwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), lstm_threads(H), LstmSmem::bwd_bytes(H), st, d_h_seq, reset, w_h, T, E,
+                                H, (const float*)ws.cp_seq, (const float*)ws.gi_, (const float*)ws.gf_, (const float*)ws.gg_, (const float*)ws.go_,
+                                (const float*)ws.tc_, d_gi, d_carry0));
+    STX_LAUNCH_OK();
+  }
+  for (int t = T - 1; t >= 0 && !clustered; --t) {
     const bool last = (t == T - 1);
     lstm_gate_bwd_kernel<<<blocks, 256, 0, st>>>(d_h_seq + (size_t)t * eh, last ? nullptr : ws.dhp_gemm, last ? nullptr : ws.dcp[(t + 1) & 1],
                                                   last ? nullptr : reset + (size_t)(t + 1) * E, ws.gi_ + (size_t)t * eh, ws.gf_ + (size_t)t * eh,
@@ -654,7 +937,7 @@ extern "C" int stx_lstm_sequence_backward(const float* d_h_seq, const uint8_t* r
       STX_CUDA_OK(simt::launch_gemm<simt::DX>(d, 1, st));
     }
   }
-  if (d_carry0) {
+  if (d_carry0 && !clustered) {
     lstm_dcarry_kernel<<<blocks, 256, 0, st>>>(ws.dhp_gemm, ws.dcp[0], reset, E, H, d_carry0);
     STX_LAUNCH_OK();
   }

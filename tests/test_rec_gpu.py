@@ -228,8 +228,22 @@ def test_experiment_runs_on_cartpole():
     assert np.isfinite(rec_ppo.run_experiment(cfg))
 
 
-@pytest.mark.parametrize("T,E,H", [(6, 40, 12), (1, 64, 128), (9, 130, 32)])
-def test_lstm_sequence_matches_oracle(T, E, H):
+@pytest.mark.parametrize("cluster", ["1", "0"])
+@pytest.mark.parametrize("T,E,H", [(6, 40, 12), (1, 64, 128), (9, 130, 32), (40, 131, 128), (3, 2050, 128)])
+def test_lstm_sequence_matches_oracle(T, E, H, cluster):
+    """cluster = "1": the persistent form on 2-CTA thread-block clusters (half of the hidden units and of W_h per CTA, h exchanged
+    through distributed shared memory every step; the default); "0": one GEMM + one gate kernel per step (fallback)."""
+    import os, subprocess, sys
+    if cluster == "0":   # the switch is read once per process: run this case in a child
+        code = ("import os; os.environ['STX_LSTM_CLUSTER']='0'; import sys; sys.path.insert(0, os.getcwd());"
+                f"import tests.test_rec_gpu as m; m._lstm_case({T}, {E}, {H}); print('child-ok')")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert "child-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    _lstm_case(T, E, H)
+
+
+def _lstm_case(T, E, H):
     from stoix_b200 import ops
 
     rng = np.random.default_rng(T * 10 + H)
