@@ -60,7 +60,7 @@ def main():
         torch.cuda.synchronize()
         phase[name] = s.elapsed_time(e)
     steps = a.envs * a.rollout
-    print(json.dumps({"metric": "env steps/sec rec_ppo Anakin (synthetic Box, GRU actor-critic)", "value": steps / ms * 1e3, "unit": "env_steps/s",
+    print(json.dumps({"metric": f"env steps/sec rec_ppo Anakin (synthetic Box, {a.cell.upper()} actor-critic)", "value": steps / ms * 1e3, "unit": "env_steps/s",
                       "ms_per_update": ms, "n_gpus": 1, "phase_ms": phase, "stx_launches_per_update": launches,
                       "config": {"workload": f"rec_ppo, obs_dim=32, envs={a.envs}, rollout={a.rollout}, epochs={a.epochs}, minibatches={a.minibatches}, "
                                              f"pre MLP[128] silu -> {a.cell.upper()}(128) -> post MLP[128] silu, fp32", "dtype": "f32", "cuda_graph": bool(cfg.arch.get("cuda_graph", True)), "phase_ms_note": "phases timed eagerly, ms_per_update from graph replays"}}))

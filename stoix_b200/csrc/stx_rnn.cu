@@ -739,6 +739,7 @@ inline cudaError_t launch_cluster2(void (*kernel)(Args...), unsigned clusters, i
 }
 
 constexpr size_t kGruSmemLimit = 227 * 1024;
+constexpr int kPersistentMinT = 4;   // below: one GEMM + one gate kernel per step
 // launch shape: R = 8 rows per CTA from 1024 sequences up (the rollout step), else 4 with the reduction split over two thread groups
 inline int gru_threads(int H, int ks) { return ((ks * 3 * H + 31) / 32) * 32; }
 inline bool gru_persistent_ok(int H) {
@@ -776,7 +777,8 @@ extern "C" int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, c
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  if (gru_persistent_ok(H)) {
+  // short sequences (the rollout's T = 1 step over all envs) do not amortise filling shared memory with W_h: per-step form
+  if (gru_persistent_ok(H) && T >= kPersistentMinT) {
     if (E >= 1024) {
       if (int rc = gru_opt_in(gru_seq_fwd_kernel<8, 1>)) return rc;
       gru_seq_fwd_kernel<8, 1><<<(unsigned)((E + 7) / 8), gru_threads(H, 1), GruSmem<8, 1>::fwd_bytes(H), st>>>(gi, reset, h0, w_h, b_hn, T, E, H, h_seq, ws.hp_seq,
@@ -817,7 +819,7 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  const bool persistent = gru_persistent_ok(H);
+  const bool persistent = gru_persistent_ok(H) && T >= kPersistentMinT;
   if (persistent) {
     if (E >= 1024) {
       if (int rc = gru_opt_in(gru_seq_bwd_kernel<8, 1>)) return rc;
@@ -883,7 +885,7 @@ extern "C" int stx_lstm_sequence_forward(const float* gi, const uint8_t* reset, 
   LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  if (lstm_cluster_ok(H, E)) {
+  if (lstm_cluster_ok(H, E) && T >= kPersistentMinT) {
     STX_CUDA_OK(launch_cluster2(lstm_seq_fwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), lstm_threads(H), LstmSmem::fwd_bytes(H), st, gi, reset, carry0, w_h,
                                 T, E, H, h_seq, carry_last, ws.hp_seq, ws.cp_seq, ws.gi_, ws.gf_, ws.gg_, ws.go_, ws.tc_));
     STX_LAUNCH_OK();
@@ -916,7 +918,7 @@ extern "C" int stx_lstm_sequence_backward(const float* d_h_seq, const uint8_t* r
   LstmWs ws = carve_lstm(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  const bool clustered = lstm_cluster_ok(H, E);
+  const bool clustered = lstm_cluster_ok(H, E) && T >= kPersistentMinT;
   if (clustered) {
     STX_CUDA_OK(launch_cluster2(lstm_seq_bwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), lstm_threads(H), LstmSmem::bwd_bytes(H), st, d_h_seq, reset, w_h, T, E,
                                 H, (const float*)ws.cp_seq, (const float*)ws.gi_, (const float*)ws.gf_, (const float*)ws.gg_, (const float*)ws.go_,
