@@ -184,6 +184,7 @@ def test_update_steps_match_oracle(chunk, cell):
         np.testing.assert_allclose(f64(sh.value[:T]), val, rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(f64(sh.log_prob), lp, rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(f64(sh.h_actor), hs_a, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(f64(sh.h_critic), hs_c, rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(f64(sh.value[T]), last_val, rtol=2e-4, atol=2e-5)
         traj = R.RecTrajectory(obs=obs[:T], done=done[:T], truncated=trunc[:T], action=action, value=f64(sh.value[:T]), reward=reward, log_prob=f64(sh.log_prob),
                                h_actor=f64(sh.h_actor), h_critic=f64(sh.h_critic), last_val=f64(sh.value[T]))
