@@ -13,6 +13,11 @@
 
 namespace stx {
 
+// acc.{x,y} += w * v.{x,y} as ONE instruction (sm_100 FFMA2 with a scalar-broadcast operand): two IEEE fused multiply-adds, the
+// same bits as two FFMAs, half the issue slots -- what the issue-bound fp32 inner loops (small GEMMs, recurrent products) need.
+__device__ __forceinline__ void fma2(float2& acc, float w, float2 v) { acc = __ffma2_rn(make_float2(w, w), v, acc); }
+
+
 // ---- error plumbing -----------------------------------------------------------------------
 void set_error(const char* fmt, ...);  // defined in stx_api.cu (thread-local buffer)
 

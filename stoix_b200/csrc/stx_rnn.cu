@@ -211,9 +211,9 @@ __global__ void __launch_bounds__(1024, 1)
     }
     // ---- (R x H) @ (H x 3H), this group's share of k ----
     if (kh < KS) {
-      float acc[R];
+      float2 acc[R / 2];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      for (int r = 0; r < R / 2; ++r) acc[r] = make_float2(0.f, 0.f);
       const float* wcol = Ws + n;
 #pragma unroll 4
       for (int k = k_begin; k < k_end; ++k) {
@@ -222,12 +222,11 @@ __global__ void __launch_bounds__(1024, 1)
 #pragma unroll
         for (int r4 = 0; r4 < R; r4 += 4) {
           const float4 hv = *reinterpret_cast<const float4*>(hk + r4);
-          acc[r4] = fmaf(w, hv.x, acc[r4]), acc[r4 + 1] = fmaf(w, hv.y, acc[r4 + 1]);
-          acc[r4 + 2] = fmaf(w, hv.z, acc[r4 + 2]), acc[r4 + 3] = fmaf(w, hv.w, acc[r4 + 3]);
+          fma2(acc[r4 / 2], w, make_float2(hv.x, hv.y)), fma2(acc[r4 / 2 + 1], w, make_float2(hv.z, hv.w));
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) ghp[((size_t)kh * R + r) * n3 + n] = acc[r];
+      for (int r = 0; r < R / 2; ++r) ghp[((size_t)kh * R + 2 * r) * n3 + n] = acc[r].x, ghp[((size_t)kh * R + 2 * r + 1) * n3 + n] = acc[r].y;
     }
     __syncthreads();
     // ---- gates: consecutive threads -> consecutive hidden units of one row ----
@@ -333,9 +332,9 @@ __global__ void __launch_bounds__(1024, 1)
       const int k = threadIdx.x % H, blk = threadIdx.x / H;
       const int gate = blk / KS, sub = blk % KS;                 // block = (gate, sub-range of its H columns)
       const int c0 = gate * H + sub * kcol, c1 = (sub * kcol + kcol < H) ? c0 + kcol : gate * H + H;
-      float acc[R];
+      float2 acc[R / 2];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      for (int r = 0; r < R / 2; ++r) acc[r] = make_float2(0.f, 0.f);
       const float* wrow = Ws + (size_t)k * (n3 + 1);
 #pragma unroll 4
       for (int nn = c0; nn < c1; ++nn) {
@@ -343,12 +342,11 @@ __global__ void __launch_bounds__(1024, 1)
 #pragma unroll
         for (int r4 = 0; r4 < R; r4 += 4) {
           const float4 dv = *reinterpret_cast<const float4*>(dgT + (size_t)nn * R + r4);
-          acc[r4] = fmaf(w, dv.x, acc[r4]), acc[r4 + 1] = fmaf(w, dv.y, acc[r4 + 1]);
-          acc[r4 + 2] = fmaf(w, dv.z, acc[r4 + 2]), acc[r4 + 3] = fmaf(w, dv.w, acc[r4 + 3]);
+          fma2(acc[r4 / 2], w, make_float2(dv.x, dv.y)), fma2(acc[r4 / 2 + 1], w, make_float2(dv.z, dv.w));
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
+      for (int r = 0; r < R / 2; ++r) part[((size_t)blk * R + 2 * r) * H + k] = acc[r].x, part[((size_t)blk * R + 2 * r + 1) * H + k] = acc[r].y;
     }
     __syncthreads();
 #pragma unroll
@@ -562,16 +560,15 @@ __global__ void __launch_bounds__(1024, 1)
       cut = (t + 1 < T) && reset[(int64_t)(t + 1) * E + rowg] != 0;
     }
     if (kh < KS) {
-      float acc[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
       const float* wcol = Ws + n;
 #pragma unroll 4
       for (int k = k_begin; k < k_end; ++k) {
         const float w = wcol[(size_t)k * (nl + 1)];
         const float4 hv = *reinterpret_cast<const float4*>(hcur + k * R);
-        acc[0] = fmaf(w, hv.x, acc[0]), acc[1] = fmaf(w, hv.y, acc[1]), acc[2] = fmaf(w, hv.z, acc[2]), acc[3] = fmaf(w, hv.w, acc[3]);
+        fma2(a01, w, make_float2(hv.x, hv.y)), fma2(a23, w, make_float2(hv.z, hv.w));
       }
+      const float acc[R] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
       for (int r = 0; r < R; ++r) ghp[((size_t)kh * R + r) * nl + n] = acc[r];
     }
@@ -671,16 +668,15 @@ __global__ void __launch_bounds__(1024, 1)
     if ((int)threadIdx.x < NB * H) {           // partial d(z) W^T over this CTA's columns, for ALL H outputs k
       const int k = threadIdx.x % H, blk = threadIdx.x / H;
       const int c0 = blk * kcol, c1 = (c0 + kcol < nl) ? c0 + kcol : nl;
-      float acc[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
       const float* wrow = Ws + (size_t)k * (nl + 1);
 #pragma unroll 4
       for (int nn = c0; nn < c1; ++nn) {
         const float w = wrow[nn];
         const float4 dv = *reinterpret_cast<const float4*>(dzT + (size_t)nn * R);
-        acc[0] = fmaf(w, dv.x, acc[0]), acc[1] = fmaf(w, dv.y, acc[1]), acc[2] = fmaf(w, dv.z, acc[2]), acc[3] = fmaf(w, dv.w, acc[3]);
+        fma2(a01, w, make_float2(dv.x, dv.y)), fma2(a23, w, make_float2(dv.z, dv.w));
       }
+      const float acc[R] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
       for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
     }

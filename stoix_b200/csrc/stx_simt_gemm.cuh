@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i) {   // FFMA2: 8 instructions for the 4x4 tile (same bits as 16 FFMAs)
+        float2 lo = make_float2(acc[i][0], acc[i][1]), hi = make_float2(acc[i][2], acc[i][3]);
+        fma2(lo, a[i], make_float2(b[0], b[1])), fma2(hi, a[i], make_float2(b[2], b[3]));
+        acc[i][0] = lo.x, acc[i][1] = lo.y, acc[i][2] = hi.x, acc[i][3] = hi.y;
+      }
       if (MODE == DW) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) dbacc[j] += b[j];
@@ -337,16 +339,19 @@ __global__ void __launch_bounds__(kPanelThreads) gemm_panel_kernel(GemmArgs g) {
       if (kk < kc) Bs[kk * kBsLd + nn] = vb[u];
     }
     __syncthreads();
+    float2 acc2[PTM][PTN / 2];
+#pragma unroll
+    for (int i = 0; i < PTM; ++i) acc2[i][0] = make_float2(acc[i][0], acc[i][1]), acc2[i][1] = make_float2(acc[i][2], acc[i][3]);
 #pragma unroll 8
     for (int kk = half; kk < kc; kk += 2) {
       const float2 a = *reinterpret_cast<const float2*>(As + kk * kAsLd + ty * PTM);
       const float4 b = *reinterpret_cast<const float4*>(Bs + kk * kBsLd + tx * PTN);
-      acc[0][0] = fmaf(a.x, b.x, acc[0][0]), acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-      acc[0][2] = fmaf(a.x, b.z, acc[0][2]), acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
-      acc[1][0] = fmaf(a.y, b.x, acc[1][0]), acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-      acc[1][2] = fmaf(a.y, b.z, acc[1][2]), acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      fma2(acc2[0][0], a.x, make_float2(b.x, b.y)), fma2(acc2[0][1], a.x, make_float2(b.z, b.w));   // FFMA2: 4 instructions for the 2x4 tile
+      fma2(acc2[1][0], a.y, make_float2(b.x, b.y)), fma2(acc2[1][1], a.y, make_float2(b.z, b.w));
       if (MODE == DW) dbacc[0] += b.x, dbacc[1] += b.y, dbacc[2] += b.z, dbacc[3] += b.w;
     }
+#pragma unroll
+    for (int i = 0; i < PTM; ++i) acc[i][0] = acc2[i][0].x, acc[i][1] = acc2[i][0].y, acc[i][2] = acc2[i][1].x, acc[i][3] = acc2[i][1].y;
     __syncthreads();
   }
 
