@@ -491,9 +491,7 @@ __device__ __forceinline__ void fb_role(uint8_t* smem_raw, const CUtensorMap& tm
           for (int g = 0; g < 4; ++g) {
 #pragma unroll
             for (int j = 4 * g; j < 4 * g + 4; ++j) {
-              const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
-              const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
-              pk[j] = pack_bf16(v0, v1);
+              pk[j] = bias_relu_pack_bf16(r[2 * j], r[2 * j + 1], *reinterpret_cast<const float2*>(bias + c * 32 + 2 * j));
             }
             STX_FLUSH_PENDING(g);  // one 512-byte store of the previous chunk (32 lanes = 32 consecutive rows)
           }

@@ -317,9 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias[c * 32 + 2 * j], 0.f);
-            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.f);
-            pk[j] = pack_bf16(v0, v1);
+            pk[j] = bias_relu_pack_bf16(r[2 * j], r[2 * j + 1], *reinterpret_cast<const float2*>(bias + c * 32 + 2 * j));
           }
           tmem_st16(ta + c * 16, pk);
           tmem_st_wait();
