@@ -486,9 +486,9 @@ struct LstmSmem {
   }
 };
 
-// this CTA's 2H columns of W_h: local column g * Hq + jl  <->  global column g * H + q * Hq + jl
-__device__ __forceinline__ void lstm_load_w(float* __restrict__ Ws, const float* __restrict__ w_h, int H, int q) {
-  const int Hq = H / 2, nl = 2 * H, total = H * nl;
+// this CTA's G * H / 2 columns of W_h (G gates): local column g * Hq + jl  <->  global column g * H + q * Hq + jl
+__device__ __forceinline__ void cluster_load_w(float* __restrict__ Ws, const float* __restrict__ w_h, int H, int q, int G) {
+  const int Hq = H / 2, nl = G * Hq, total = H * nl;
   constexpr int U = 8;
   for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
     float v[U];
@@ -497,7 +497,7 @@ __device__ __forceinline__ void lstm_load_w(float* __restrict__ Ws, const float*
       const int i = base + u * blockDim.x;
       if (i < total) {
         const int k = i / nl, c = i % nl;
-        v[u] = __ldg(w_h + (size_t)k * 4 * H + (c / Hq) * H + q * Hq + c % Hq);
+        v[u] = __ldg(w_h + (size_t)k * G * H + (c / Hq) * H + q * Hq + c % Hq);
       }
     }
 #pragma unroll
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(1024, 1)
   const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
   const int items = Hq * R;
   const int64_t eh = E * (int64_t)H;
-  lstm_load_w(Ws, w_h, H, q);
+  cluster_load_w(Ws, w_h, H, q, 4);
   for (int i = threadIdx.x; i < H * R; i += blockDim.x) {     // every CTA initialises the FULL h of buffer 0 itself
     const int r = i / H, j = i % H;
     const int64_t row = row0 + r;
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(1024, 1)
   const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
   const int64_t eh = E * (int64_t)H;
   const int items = Hq * R;
-  lstm_load_w(Ws, w_h, H, q);
+  cluster_load_w(Ws, w_h, H, q, 4);
   for (int i = threadIdx.x; i < items; i += blockDim.x) dh_rec[i] = 0.f, dc_rec[i] = 0.f;
   const int i0 = threadIdx.x;
   const int r0 = i0 / Hq, jl0 = i0 % Hq;
@@ -710,6 +710,209 @@ __global__ void __launch_bounds__(1024, 1)
   cluster.sync();   // no CTA exits while its peer may still write into its shared memory
 }
 
+// ---- GRU on 2-CTA clusters: the same split (half of the hidden units, 3 H / 2 gate columns and 99 KB of W_h per CTA) halves the
+// issue-bound per-step product of gru_seq_*_kernel; used for the training sequences (T >= kPersistentMinT, rows < 1024).
+struct GruClSmem {
+  __host__ __device__ static size_t w_floats(int H) { return ((size_t)H * (3 * (H / 2) + 1) + 3) / 4 * 4; }
+  static size_t fwd_bytes(int H) { return (w_floats(H) + 2 * (size_t)H * kLstmR + (size_t)kLstmKS * kLstmR * 3 * (H / 2)) * 4; }
+  static size_t bwd_bytes(int H) { return (w_floats(H) + (size_t)3 * (H / 2) * kLstmR + 3 * (size_t)kLstmR * H + 3 * (size_t)kLstmR * (H / 2)) * 4; }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+    gru_cl_fwd_kernel(const float* __restrict__ gi, const uint8_t* __restrict__ reset, const float* __restrict__ h0, const float* __restrict__ w_h,
+                      const float* __restrict__ b_hn, int T, int64_t E, int H, float* __restrict__ h_seq, float* __restrict__ hp_seq,
+                      float* __restrict__ rs, float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ ghns) {
+  constexpr int R = kLstmR, KS = kLstmKS;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  extern __shared__ __align__(16) float gsm[];
+  const int Hq = H / 2, nl = 3 * Hq;
+  float* Ws = gsm;                                  // [H][nl + 1]
+  float* hs = Ws + GruClSmem::w_floats(H);          // [2][H][R]
+  float* ghp = hs + 2 * (size_t)H * R;              // [KS][R][nl]
+  float* hs_peer = cluster.map_shared_rank(hs, q ^ 1);
+  const int kh = threadIdx.x / nl, n = threadIdx.x % nl;
+  const int kper = (H + KS - 1) / KS;
+  const int k_begin = kh * kper, k_end = (k_begin + kper < H) ? k_begin + kper : H;
+  const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
+  const int items = Hq * R;
+  const int64_t eh = E * (int64_t)H;
+  cluster_load_w(Ws, w_h, H, q, 3);
+  for (int i = threadIdx.x; i < H * R; i += blockDim.x) {
+    const int r = i / H, j = i % H;
+    const int64_t row = row0 + r;
+    float hv = 0.f;
+    if (row < E && !reset[row]) hv = h0[row * H + j];
+    hs[j * R + r] = hv;
+    if (row < E && j / Hq == q) hp_seq[row * H + j] = hv;
+  }
+  cluster.sync();
+  const int i0 = threadIdx.x;
+  const int r0 = i0 / Hq, jl0 = i0 % Hq;
+  const int64_t rowg = row0 + r0;
+  const int j0 = q * Hq + jl0;
+  for (int t = 0; t < T; ++t) {
+    const float* hcur = hs + (size_t)(t & 1) * H * R;
+    const size_t nxt = (size_t)((t + 1) & 1) * H * R;
+    float g3[3] = {0.f, 0.f, 0.f}, bh = 0.f;
+    bool cut = false;
+    if (i0 < items && rowg < E) {
+      const float* a = gi + ((int64_t)t * E + rowg) * 3 * H + j0;
+      g3[0] = __ldg(a), g3[1] = __ldg(a + H), g3[2] = __ldg(a + 2 * H), bh = __ldg(b_hn + j0);
+      cut = (t + 1 < T) && reset[(int64_t)(t + 1) * E + rowg] != 0;
+    }
+    if (kh < KS) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+      const float* wcol = Ws + n;
+#pragma unroll 4
+      for (int k = k_begin; k < k_end; ++k) {
+        const float w = wcol[(size_t)k * (nl + 1)];
+        const float4 hv = *reinterpret_cast<const float4*>(hcur + k * R);
+        fma2(a01, w, make_float2(hv.x, hv.y)), fma2(a23, w, make_float2(hv.z, hv.w));
+      }
+      const float acc[R] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+      for (int r = 0; r < R; ++r) ghp[((size_t)kh * R + r) * nl + n] = acc[r];
+    }
+    __syncthreads();
+    if (i0 < items) {
+      float hn = 0.f;
+      if (rowg < E) {
+        float b[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float v = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) v += ghp[((size_t)kk * R + r0) * nl + g * Hq + jl0];   // fixed order
+          b[g] = v;
+        }
+        const float rg = sigm(g3[0] + b[0]), zg = sigm(g3[1] + b[1]);
+        const float ghn = b[2] + bh;
+        const float ng = tanhf(g3[2] + rg * ghn);
+        const float hpv = hcur[j0 * R + r0];
+        const float h = (1.f - zg) * ng + zg * hpv;
+        const int64_t o = (int64_t)t * eh + rowg * H + j0;
+        h_seq[o] = h, rs[o] = rg, zs[o] = zg, ns[o] = ng, ghns[o] = ghn;
+        hn = cut ? 0.f : h;
+        hp_seq[o + eh] = hn;
+      }
+      hs[nxt + (size_t)j0 * R + r0] = hn;
+      hs_peer[nxt + (size_t)j0 * R + r0] = hn;
+    }
+    cluster.sync();
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    gru_cl_bwd_kernel(const float* __restrict__ d_h_seq, const uint8_t* __restrict__ reset, const float* __restrict__ w_h, int T, int64_t E, int H,
+                      const float* __restrict__ hp_seq, const float* __restrict__ rs, const float* __restrict__ zs, const float* __restrict__ ns,
+                      const float* __restrict__ ghns, float* __restrict__ d_gi, float* __restrict__ d_gh_seq, float* __restrict__ d_h0) {
+  constexpr int R = kLstmR;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  extern __shared__ __align__(16) float gsm[];
+  const int Hq = H / 2, nl = 3 * Hq;
+  constexpr int NB = 3;                             // column blocks of this CTA's 3 Hq columns (one gate each)
+  float* Ws = gsm;                                  // [H][nl + 1]
+  float* dgT = Ws + GruClSmem::w_floats(H);         // [nl][R]
+  float* part = dgT + (size_t)nl * R;               // [NB][R][H]
+  float* inbox = part + (size_t)NB * R * H;         // [2][R][Hq]
+  float* dh_rec = inbox + 2 * (size_t)R * Hq;       // [R][Hq]
+  float* inbox_peer = cluster.map_shared_rank(inbox, q ^ 1);
+  const int64_t row0 = (int64_t)(blockIdx.x / 2) * R;
+  const int64_t eh = E * (int64_t)H;
+  const int items = Hq * R;
+  cluster_load_w(Ws, w_h, H, q, 3);
+  for (int i = threadIdx.x; i < items; i += blockDim.x) dh_rec[i] = 0.f;
+  const int i0 = threadIdx.x;
+  const int r0 = i0 / Hq, jl0 = i0 % Hq;
+  const int64_t rowg = row0 + r0;
+  const int j0 = q * Hq + jl0;
+  float v_dh = 0.f, v_r = 0.f, v_z = 0.f, v_n = 0.f, v_g = 0.f, v_hp = 0.f;
+  bool v_cut = false;
+  auto request = [&](int t) {
+    v_dh = v_r = v_z = v_n = v_g = v_hp = 0.f, v_cut = false;
+    if (i0 < items && rowg < E && t >= 0) {
+      const int64_t o = (int64_t)t * eh + rowg * H + j0;
+      v_dh = __ldg(d_h_seq + o), v_r = __ldg(rs + o), v_z = __ldg(zs + o), v_n = __ldg(ns + o), v_g = __ldg(ghns + o), v_hp = __ldg(hp_seq + o);
+      v_cut = reset[(int64_t)t * E + rowg] != 0;
+    }
+  };
+  request(T - 1);
+  cluster.sync();
+  for (int t = T - 1; t >= 0; --t) {
+    const bool cut_t = v_cut;
+    float direct = 0.f;
+    if (i0 < items) {
+      float dpr = 0.f, dpz = 0.f, dpn = 0.f, rg = 0.f;
+      if (rowg < E) {
+        const float dh = v_dh + dh_rec[r0 * Hq + jl0];
+        rg = v_r;
+        const float dn = dh * (1.f - v_z), dz = dh * (v_hp - v_n);
+        dpn = dn * (1.f - v_n * v_n);
+        dpr = dpn * v_g * rg * (1.f - rg);
+        dpz = dz * v_z * (1.f - v_z);
+        direct = dh * v_z;
+        float* a = d_gi + ((int64_t)t * E + rowg) * 3 * H + j0;
+        float* b = d_gh_seq + ((int64_t)t * E + rowg) * 3 * H + j0;
+        a[0] = dpr, a[H] = dpz, a[2 * H] = dpn;
+        b[0] = dpr, b[H] = dpz, b[2 * H] = dpn * rg;
+      }
+      dgT[(size_t)jl0 * R + r0] = dpr, dgT[(size_t)(Hq + jl0) * R + r0] = dpz, dgT[(size_t)(2 * Hq + jl0) * R + r0] = dpn * rg;
+    }
+    request(t - 1);
+    __syncthreads();
+    if ((int)threadIdx.x < NB * H) {
+      const int k = threadIdx.x % H, blk = threadIdx.x / H;
+      const int c0 = blk * Hq, c1 = c0 + Hq;
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+      const float* wrow = Ws + (size_t)k * (nl + 1);
+#pragma unroll 4
+      for (int nn = c0; nn < c1; ++nn) {
+        const float w = wrow[nn];
+        const float4 dv = *reinterpret_cast<const float4*>(dgT + (size_t)nn * R);
+        fma2(a01, w, make_float2(dv.x, dv.y)), fma2(a23, w, make_float2(dv.z, dv.w));
+      }
+      const float acc[R] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+      for (int r = 0; r < R; ++r) part[((size_t)blk * R + r) * H + k] = acc[r];
+    }
+    __syncthreads();
+    float mine = 0.f;
+    float* box = inbox + (size_t)(t & 1) * R * Hq;
+    if (i0 < items) {
+      float other = 0.f;
+      const int jp = (q ^ 1) * Hq + jl0;
+#pragma unroll
+      for (int blk = 0; blk < NB; ++blk) {   // fixed order
+        mine += part[((size_t)blk * R + r0) * H + j0];
+        other += part[((size_t)blk * R + r0) * H + jp];
+      }
+      inbox_peer[(size_t)(t & 1) * R * Hq + r0 * Hq + jl0] = other;
+    }
+    cluster.sync();
+    if (i0 < items) {
+      const float theirs = box[r0 * Hq + jl0];
+      const float dhp = direct + ((q == 0) ? (mine + theirs) : (theirs + mine));   // rank-0 partial first on both CTAs
+      dh_rec[r0 * Hq + jl0] = (rowg < E && !cut_t) ? dhp : 0.f;
+    }
+    __syncthreads();
+  }
+  if (d_h0 && i0 < items && rowg < E) d_h0[rowg * H + j0] = dh_rec[r0 * Hq + jl0];
+  cluster.sync();
+}
+
+inline int gru_cl_threads(int H) { return ((kLstmKS * 3 * (H / 2) + 31) / 32) * 32; }
+inline bool gru_cluster_ok(int H, int64_t E, int T) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("STX_GRU_CLUSTER");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return enabled && E < 1024 && T >= 4 && H >= 2 && H % 2 == 0 && gru_cl_threads(H) <= 1024 && (H / 2) * kLstmR <= gru_cl_threads(H) &&
+         3 * H <= gru_cl_threads(H) && GruClSmem::fwd_bytes(H) <= 227 * 1024 && GruClSmem::bwd_bytes(H) <= 227 * 1024;
+}
+
 inline int lstm_threads(int H) { return ((kLstmKS * 2 * H + 31) / 32) * 32; }
 inline bool lstm_cluster_ok(int H, int64_t E) {
   static int enabled = -1;
@@ -773,6 +976,12 @@ extern "C" int stx_gru_sequence_forward(const float* gi, const uint8_t* reset, c
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
+  if (gru_cluster_ok(H, E, T)) {   // training sequences: 2-CTA clusters, half of the gate columns per CTA
+    STX_CUDA_OK(launch_cluster2(gru_cl_fwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), gru_cl_threads(H), GruClSmem::fwd_bytes(H), st, gi, reset, h0, w_h, b_hn,
+                                T, E, H, h_seq, ws.hp_seq, ws.r, ws.z, ws.n, ws.ghn));
+    STX_LAUNCH_OK();
+    return STX_OK;
+  }
   // short sequences (the rollout's T = 1 step over all envs) do not amortise filling shared memory with W_h: per-step form
   if (gru_persistent_ok(H) && T >= kPersistentMinT) {
     if (E >= 1024) {
@@ -815,8 +1024,14 @@ extern "C" int stx_gru_sequence_backward(const float* d_h_seq, const uint8_t* re
   GruWs ws = carve_gru(T, E, H, reinterpret_cast<char*>(workspace));
   const size_t eh = (size_t)E * H;
   const unsigned blocks = (unsigned)((eh + 255) / 256);
-  const bool persistent = gru_persistent_ok(H) && T >= kPersistentMinT;
-  if (persistent) {
+  const bool clustered = gru_cluster_ok(H, E, T);
+  const bool persistent = clustered || (gru_persistent_ok(H) && T >= kPersistentMinT);
+  if (clustered) {
+    STX_CUDA_OK(launch_cluster2(gru_cl_bwd_kernel, (unsigned)((E + kLstmR - 1) / kLstmR), gru_cl_threads(H), GruClSmem::bwd_bytes(H), st, d_h_seq, reset, w_h, T, E, H,
+                                (const float*)ws.hp_seq, (const float*)ws.r, (const float*)ws.z, (const float*)ws.n, (const float*)ws.ghn, d_gi, ws.d_gh_seq,
+                                d_h0));
+    STX_LAUNCH_OK();
+  } else if (persistent) {
     if (E >= 1024) {
       if (int rc = gru_opt_in(gru_seq_bwd_kernel<8, 1>)) return rc;
       gru_seq_bwd_kernel<8, 1><<<(unsigned)((E + 7) / 8), gru_threads(H, 1), GruSmem<8, 1>::bwd_bytes(H), st>>>(d_h_seq, reset, w_h, T, E, H, ws.hp_seq, ws.r, ws.z,

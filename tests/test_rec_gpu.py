@@ -21,14 +21,15 @@ dev = lambda x, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(x), devic
 rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("persistent", ["1", "0"])
+@pytest.mark.parametrize("persistent", ["cluster", "1", "0"])
 @pytest.mark.parametrize("T,E,H", [(7, 33, 20), (1, 64, 128), (16, 300, 128), (5, 1030, 6), (40, 130, 128)])
 def test_gru_sequence_matches_oracle(T, E, H, persistent):
-    """persistent = "1": one CTA per 4 / 8 sequences for all T steps with W_h resident in shared memory (the default);
-    "0": the per-step form (a GEMM + a gate kernel per step), kept as the fallback for hidden sizes whose W_h does not fit."""
+    """"cluster" (default): 2-CTA thread-block clusters, half of the hidden units / gate columns per CTA, h through distributed shared
+    memory (sequences of >= 4 steps, < 1024 rows); "1": one CTA per 4 / 8 sequences with the whole W_h in its shared memory;
+    "0": the per-step form (a GEMM + a gate kernel per step), the fallback for hidden sizes whose W_h does not fit."""
     import subprocess, sys, os
-    if persistent == "0":   # the switch is read once per process: run this case in a child
-        code = ("import os; os.environ['STX_GRU_PERSISTENT']='0'; import sys; sys.path.insert(0, os.getcwd());"
+    if persistent != "cluster":   # the switches are read once per process: run these cases in a child
+        code = (f"import os; os.environ['STX_GRU_CLUSTER']='0'; os.environ['STX_GRU_PERSISTENT']='{persistent}'; import sys; sys.path.insert(0, os.getcwd());"
                 f"import tests.test_rec_gpu as m; m._gru_case({T}, {E}, {H}); print('child-ok')")
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert "child-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
