@@ -172,7 +172,7 @@ class MultiNetwork:
 
 def __getattr__(name):   # stoix.networks.base.{ScannedRNN, RecurrentActor, RecurrentCritic} (base.py:124-222) live in recurrent.py
     if name in ("ScannedRNN", "RecurrentActor", "RecurrentCritic"):
-        from . import recurrent
+        from stoix_b200.networks import recurrent
 
         return getattr(recurrent, name)
     raise AttributeError(name)

@@ -100,3 +100,60 @@ def test_oracle_update_is_invariant_to_the_shard_axis_layout():
                        truncation_t=trunc[:, e : e + 1], time_major=True, standardize_advantages=False)
         np.testing.assert_allclose(adv[:, e], a1[:, 0], rtol=1e-12)
         np.testing.assert_allclose(tgt[:, e], t1[:, 0], rtol=1e-12)
+
+
+def test_next_row_configs_compose_and_resolve_targets():
+    """default_rec_ppo / default_ff_sac / sebulba default_ff_ppo: the reference's group names, `_target_: stoix.*` strings resolve to the
+    stoix_b200 classes (also through the `stoix` alias package), shape derivation fills the derived fields."""
+    import stoix.networks.base as ref_base
+    from stoix_b200.config import compose, instantiate
+    from stoix_b200.networks import recurrent
+    from stoix_b200.utils.total_timestep_checker import check_total_timesteps
+
+    assert ref_base.ScannedRNN is recurrent.ScannedRNN and ref_base.RecurrentActor is recurrent.RecurrentActor
+    c = compose("default_rec_ppo", ["arch.total_num_envs=64", "system.rollout_length=16", "arch.total_timesteps=4096"], config_dir="default/anakin")
+    assert c.system.system_name == "rec_ppo" and c.system.recurrent_chunk_size is None and c.network.actor_network.rnn_layer.cell_type == "gru"
+    rnn = instantiate(c.network.critic_network.rnn_layer)
+    assert isinstance(rnn, recurrent.ScannedRNN) and rnn.hidden_state_dim == 128 and rnn.state_dim == 128
+    assert recurrent.ScannedRNN(32, "lstm").state_dim == 64 and recurrent.ScannedRNN(32, "optimised_lstm").cell_type == "lstm"
+    with pytest.raises(NotImplementedError):
+        recurrent.ScannedRNN(32, "mgu")
+    c.num_devices = 1
+    c = check_total_timesteps(c, quiet=True)
+    assert c.arch.num_envs == 64 and c.arch.num_updates == 4
+    s = compose("default_ff_sac", ["arch.total_num_envs=128"], config_dir="default/anakin")
+    assert s.system.tau == 0.005 and s.system.actor_lr == 3e-4 and s.network.q_network.pre_torso.use_layer_norm is True
+    head = instantiate(s.network.actor_network.action_head, action_dim=6, minimum=-1.0, maximum=1.0)
+    assert head.out_dim == 12 and head.kernel_blocks == (6, 6)
+    b = compose("default_ff_ppo", ["arch.total_num_envs=512"], config_dir="default/sebulba")
+    assert b.arch.architecture_name == "sebulba"
+
+
+def test_recurrent_and_sac_arena_layouts_match_the_oracle_flat_order():
+    """RecLayout (pre-torso | W_i | b_i | W_h | b_hn | post-torso | head) == oracle RecNet.flat(); SAC arena blocks are 8-float aligned."""
+    from oracle import ppo_oracle as O
+    from oracle import rec_oracle as R
+    from stoix_b200.networks.recurrent import RecLayout
+    from stoix_b200 import ops
+
+    rng = np.random.default_rng(0)
+    for cell, G in (("gru", 3), ("lstm", 4)):
+        D, P, H, Q, A = 12, 24, 16, 20, 5
+        lay = RecLayout(D, (P,), H, (Q,), A, "silu", False, "silu", False, cell)
+        pre = O.MLPParams([rng.standard_normal((D, P)), rng.standard_normal((P, G * H))], [rng.standard_normal(P), rng.standard_normal(G * H)], "silu")
+        post = O.MLPParams([rng.standard_normal((H, Q)), rng.standard_normal((Q, A))], [rng.standard_normal(Q), rng.standard_normal(A)], "silu")
+        net = R.RecNet(pre, rng.standard_normal((H, G * H)), rng.standard_normal(H if cell == "gru" else 0), post)
+        flat = net.flat()
+        assert flat.size == lay.param_count and lay.S == (H if cell == "gru" else 2 * H) and lay.G == G
+        np.testing.assert_array_equal(flat[lay.off_wh:lay.off_bhn].reshape(H, G * H), net.Wh)
+        np.testing.assert_array_equal(flat[lay.off_post:lay.off_post + H * Q].reshape(H, Q), post.W[0])
+        back = R.RecNet.from_flat(flat, lay.spec_pre.sizes, H, lay.spec_post.sizes, "silu")
+        np.testing.assert_array_equal(back.flat(), flat)
+        assert back.is_lstm == (cell == "lstm")
+    from stoix_b200.systems.sac.ff_sac import sac_arena_layout
+
+    sa = ops.MlpSpec((17, 256, 256, 256, 256, 12), activation="silu")
+    sq = ops.MlpSpec((23, 256, 256, 256, 256, 1), activation="silu", use_layer_norm=True)
+    lay = sac_arena_layout(sa, sq)
+    assert all(lay[k] % 8 == 0 for k in ("actor", "q1", "q2", "alpha", "total")) and lay["q1"] >= sa.param_count
+    assert lay["q2"] - lay["q1"] >= sq.param_count == 204801 and lay["q_block"] == lay["alpha"] - lay["q1"] and lay["total"] == lay["alpha"] + 8
