@@ -101,20 +101,28 @@ __device__ __forceinline__ void store_out(const GemmArgs& g, int64_t m, int n, f
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+// Register-tiled GEMM, one shared-memory stage + register prefetch: the global loads of step k+1 are issued before the products
+// of step k and land in registers while the FFMA2s run; (BM, BN, BK, TM, TN) = (64, 64, 16, 4, 4) for mid-size grids and
+// (128, 128, 8, 8, 8) -- 64 accumulators per thread, 4 shared loads per 32 packed FMAs -- when that still fills the GPU.
+template <int MODE, int BM_, int BN_, int BK_, int TM_, int TN_>
+__global__ void __launch_bounds__((BM_ / TM_) * (BN_ / TN_)) gemm_kernel(GemmArgs g) {
+  constexpr int NT = (BM_ / TM_) * (BN_ / TN_);
+  constexpr int LA = BM_ * BK_ / NT, LB = BN_ * BK_ / NT;
+  static_assert(BM_ * BK_ % NT == 0 && BN_ * BK_ % NT == 0 && TN_ % 2 == 0 && TM_ % 4 == 0 && TN_ % 4 == 0, "tile shape");
+  __shared__ __align__(16) float As[BK_][BM_ + 4];
+  __shared__ __align__(16) float Bs[BK_][BN_ + 4];
   const int tid = threadIdx.x;
-  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
-  const int64_t m0 = (int64_t)blockIdx.y * BM;  // output row tile
-  const int n0 = blockIdx.x * BN;               // output col tile
-  float acc[TM][TN];
+  const int tx = tid % (BN_ / TN_), ty = tid / (BN_ / TN_);
+  const int64_t m0 = (int64_t)blockIdx.y * BM_;  // output row tile
+  const int n0 = blockIdx.x * BN_;               // output col tile
+  float2 acc[TM_][TN_ / 2];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < TM_; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  float dbacc[TN] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < TN_ / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  float dbacc[TN_];
+#pragma unroll
+  for (int j = 0; j < TN_; ++j) dbacc[j] = 0.f;
 
   // reduction range
   int64_t r_begin = 0, r_end;
@@ -127,24 +135,21 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
   }
   const int out_rows = (MODE == DW) ? g.K : 0;  // DW: output rows = in-dim
 
-  for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
-    // All global loads of the step go to registers first (read-only path), then the shared stores: a load -> store -> load
-    // loop would serialise on the memory latency (the compiler cannot prove a generic pointer does not alias shared memory).
-    constexpr int LA = BM * BK / kThreads, LB = BN * BK / kThreads;  // 4, 4
-    float va[LA], vb[LB];
-    if (MODE == FWD || MODE == DX) {  // A[row(m)][r0 + kk]: kk fastest in memory -> As[kk][m]
+  float va[LA], vb[LB];
+  auto load_tiles = [&](int64_t r0) {   // all loads into registers (read-only path): nothing between them depends on shared memory
+    if (MODE == FWD || MODE == DX) {    // A[row(m)][r0 + kk]: kk fastest in memory -> As[kk][m]
 #pragma unroll
       for (int u = 0; u < LA; ++u) {
-        const int i = tid + u * kThreads, kk = i % BK, mm = i / BK;
+        const int i = tid + u * NT, kk = i % BK_, mm = i / BK_;
         const int64_t m = m0 + mm, k = r0 + kk;
         const bool ok = m < g.M && k < r_end;
         const int64_t row = ok ? ((MODE == FWD && g.rowidx) ? (int64_t)__ldg(g.rowidx + m) : m) : 0;
         va[u] = ok ? __ldg(g.A + row * g.lda + k) : 0.f;
       }
-    } else {  // DW: A(f, r) = H[row(r)][f]; f (feature) fastest in memory. As[kk = r][mm = f]
+    } else {                            // DW: A(f, r) = H[row(r)][f]; f (feature) fastest in memory. As[kk = r][mm = f]
 #pragma unroll
       for (int u = 0; u < LA; ++u) {
-        const int i = tid + u * kThreads, mm = i % BM, kk = i / BM;
+        const int i = tid + u * NT, mm = i % BM_, kk = i / BM_;
         const int64_t r = r0 + kk, f = m0 + mm;
         const bool ok = r < r_end && f < out_rows;
         const int64_t row = ok ? (g.rowidx ? (int64_t)__ldg(g.rowidx + r) : r) : 0;
@@ -153,48 +158,56 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
     }
 #pragma unroll
     for (int u = 0; u < LB; ++u) {
-      const int i = tid + u * kThreads;
-      if (MODE == DX) {  // B(kk, j) = W[j][r0 + kk], W (Kout x Nr) row-major; reduction fastest in memory
-        const int kk = i % BK, nn = i / BK;
+      const int i = tid + u * NT;
+      if (MODE == DX) {                 // B(kk, j) = W[j][r0 + kk], W (Kout x Nr) row-major; reduction fastest in memory
+        const int kk = i % BK_, nn = i / BK_;
         const int64_t k = r0 + kk;
         const int j = n0 + nn;
         vb[u] = (k < r_end && j < g.N) ? __ldg(g.B + (int64_t)j * g.K + k) : 0.f;
-      } else {           // FWD: W[k][n]; DW: dY[r][n]
-        const int nn = i % BN, kk = i / BN;
+      } else {                          // FWD: W[k][n]; DW: dY[r][n]
+        const int nn = i % BN_, kk = i / BN_;
         const int64_t k = r0 + kk;
         const int n = n0 + nn;
         vb[u] = (k < r_end && n < g.N) ? __ldg(g.B + k * g.N + n) : 0.f;
       }
     }
+  };
+  if (r_begin < r_end) load_tiles(r_begin);
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += BK_) {
 #pragma unroll
     for (int u = 0; u < LA; ++u) {
-      const int i = tid + u * kThreads;
-      if (MODE == DW) As[i / BM][i % BM] = va[u];
-      else As[i % BK][i / BK] = va[u];
+      const int i = tid + u * NT;
+      if (MODE == DW) As[i / BM_][i % BM_] = va[u];
+      else As[i % BK_][i / BK_] = va[u];
     }
 #pragma unroll
     for (int u = 0; u < LB; ++u) {
-      const int i = tid + u * kThreads;
-      if (MODE == DX) Bs[i % BK][i / BK] = vb[u];
-      else Bs[i / BN][i % BN] = vb[u];
+      const int i = tid + u * NT;
+      if (MODE == DX) Bs[i % BK_][i / BK_] = vb[u];
+      else Bs[i / BN_][i % BN_] = vb[u];
     }
     __syncthreads();
+    if (r0 + BK_ < r_end) load_tiles(r0 + BK_);   // in flight under the products below
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float a[TM], b[TN];
+    for (int kk = 0; kk < BK_; ++kk) {
+      float a[TM_], b[TN_];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {   // FFMA2: 8 instructions for the 4x4 tile (same bits as 16 FFMAs)
-        float2 lo = make_float2(acc[i][0], acc[i][1]), hi = make_float2(acc[i][2], acc[i][3]);
-        fma2(lo, a[i], make_float2(b[0], b[1])), fma2(hi, a[i], make_float2(b[2], b[3]));
-        acc[i][0] = lo.x, acc[i][1] = lo.y, acc[i][2] = hi.x, acc[i][3] = hi.y;
+      for (int i = 0; i < TM_; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * TM_ + i]);
+        a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
       }
+#pragma unroll
+      for (int j = 0; j < TN_; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN_ + j]);
+        b[j] = v.x, b[j + 1] = v.y, b[j + 2] = v.z, b[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM_; ++i)
+#pragma unroll
+        for (int j = 0; j < TN_ / 2; ++j) fma2(acc[i][j], a[i], make_float2(b[2 * j], b[2 * j + 1]));   // FFMA2: same bits as two FFMAs
       if (MODE == DW) {
 #pragma unroll
-        for (int j = 0; j < TN; ++j) dbacc[j] += b[j];
+        for (int j = 0; j < TN_; ++j) dbacc[j] += b[j];
       }
     }
     __syncthreads();
@@ -203,32 +216,32 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(GemmArgs g) {
   // ---- epilogue ----
   if (MODE != DW) {
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int64_t m = m0 + ty * TM + i;
+    for (int i = 0; i < TM_; ++i) {
+      const int64_t m = m0 + ty * TM_ + i;
       if (m >= g.M) continue;
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx * TN + j;
-        if (n < g.N) store_out<MODE>(g, m, n, acc[i][j]);
+      for (int j = 0; j < TN_; ++j) {
+        const int n = n0 + tx * TN_ + j;
+        if (n < g.N) store_out<MODE>(g, m, n, (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
       }
     }
   } else {
     float* Cp = g.C + (int64_t)blockIdx.z * g.part_stride;
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int64_t f = m0 + ty * TM + i;
+    for (int i = 0; i < TM_; ++i) {
+      const int64_t f = m0 + ty * TM_ + i;
       if (f >= out_rows) continue;
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx * TN + j;
-        if (n < g.N) Cp[f * g.N + n] = acc[i][j];
+      for (int j = 0; j < TN_; ++j) {
+        const int n = n0 + tx * TN_ + j;
+        if (n < g.N) Cp[f * g.N + n] = (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x;
       }
     }
     if (blockIdx.y == 0 && ty == 0 && g.dbias) {
       float* dbp = g.dbias + (int64_t)blockIdx.z * g.dbias_stride;
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx * TN + j;
+      for (int j = 0; j < TN_; ++j) {
+        const int n = n0 + tx * TN_ + j;
         if (n < g.N) dbp[n] = dbacc[j];
       }
     }
@@ -417,9 +430,19 @@ template <int MODE>
 inline cudaError_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
   const int64_t out_rows = (MODE == DW) ? g.K : g.M;
   const int64_t ctas64 = ((out_rows + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (MODE == DW ? splits : 1);
+  const int64_t ctas128 = ((out_rows + 127) / 128) * ((g.N + 127) / 128) * (MODE == DW ? splits : 1);
+  // 128x128x8 tiles with 8x8 outputs per thread need ~136 registers -> one 256-thread block per SM, and measured SLOWER than the
+  // 64x64x16 tiles on every workload here (fp32 PPO update 97 -> 145 ms, recurrent update +10 %): kept for reference, not dispatched
+  // (STX_GEMM_128=1 enables it).
+  static const bool big_tiles = [] { const char* e = getenv("STX_GEMM_128"); return e && e[0] == '1'; }();
+  if (big_tiles && ctas128 >= kPanelBelowCtas) {
+    dim3 grid((g.N + 127) / 128, (unsigned)((out_rows + 127) / 128), MODE == DW ? splits : 1);
+    gemm_kernel<MODE, 128, 128, 8, 8, 8><<<grid, 256, 0, st>>>(g);
+    return cudaGetLastError();
+  }
   if (ctas64 >= kPanelBelowCtas) {
     dim3 grid((g.N + BN - 1) / BN, (unsigned)((out_rows + BM - 1) / BM), MODE == DW ? splits : 1);
-    gemm_kernel<MODE><<<grid, kThreads, 0, st>>>(g);
+    gemm_kernel<MODE, BM, BN, BK, TM, TN><<<grid, kThreads, 0, st>>>(g);
     return cudaGetLastError();
   }
   static unsigned long long opted = 0;  // bit d: dynamic shared memory opt-in done on device d (per instantiation)
