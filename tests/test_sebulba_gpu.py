@@ -160,3 +160,19 @@ def test_threaded_run_completes(precision):
                                      "arch.max_eval_steps=300"], config_dir="default/sebulba")
     perf = seb.run_experiment(cfg)
     assert np.isfinite(perf)
+
+
+def test_threaded_run_with_actor_and_learner_on_different_gpus():
+    """The Sebulba split proper (configs/arch/sebulba.yaml: actor.device_ids != learner.device_ids): inference servers on cuda:0, learner on
+    cuda:1, rollouts cross by peer copy of the (T+1)-step storages, parameters come back by peer copy of the flat arena."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("NEEDS 2 GPUs: run `gpurun --gpus 2 -- python -m pytest tests/test_sebulba_gpu.py -m gpu`")
+    from stoix_b200.config import compose
+    from stoix_b200.systems.ppo.sebulba import ff_ppo as seb
+
+    for precision in ("bf16", "f32"):
+        cfg = compose("default_ff_ppo", ["arch.total_num_envs=256", "system.rollout_length=8", "system.num_minibatches=2", "arch.total_timesteps=24576",
+                                         "arch.actor.actor_per_device=2", "arch.num_evaluation=2", "arch.num_eval_episodes=8", "logger.use_console=False",
+                                         f"arch.precision={precision}", "arch.max_eval_steps=300", "arch.actor.device_ids=[0]", "arch.learner.device_ids=[1]",
+                                         "arch.evaluator_device_id=0"], config_dir="default/sebulba")
+        assert np.isfinite(seb.run_experiment(cfg))
